@@ -1,0 +1,68 @@
+"""Pin the oracle's FFT estimator against an explicit sum over closed triangles
+(the idea of the reference's own bk_binned cross-check, main.py:834-1004)."""
+import numpy as np
+import pytest
+
+from oracle import bskit_oracle as orc
+
+
+def _field(n, seed):
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((n, n, n))
+    return g + 0.4 * g ** 2 - 0.4          # non-Gaussian, so B != 0
+
+
+@pytest.mark.parametrize("n", [10, 12])
+def test_fft_estimator_equals_bruteforce_auto(n):
+    box = 100.0
+    kf = 2 * np.pi / box
+    edges = np.array([[0.5 * kf, 1.5 * kf], [1.5 * kf, 2.5 * kf], [2.5 * kf, 3.5 * kf]])
+    triples = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1], [2, 1, 1], [2, 2, 1]])
+    m = _field(n, 3)
+    b = orc.measure_unnormalized([m], box, edges, triples)
+    ntri, kmean = orc.measure_gridinfo(n, box, edges, triples)
+    for t, tr in enumerate(triples):
+        bb, cnt, km = orc.brute_force_triangle([m], box, [edges[i] for i in tr])
+        assert abs(ntri[t] - cnt) < 1e-6 * max(cnt, 1)
+        assert abs(b[t] - bb) <= 1e-11 * max(abs(bb), 1e-30)
+        np.testing.assert_allclose(kmean[t], km, rtol=1e-11)
+
+
+def test_known_triangle_counts():
+    # counts 120, 174, 456 for golden rows 0,1,2 (bins [.5,1.5],[1.5,2.5] k_f)
+    kf = 2 * np.pi / 1000.0
+    edges = np.array([[0.5 * kf, 1.5 * kf], [1.5 * kf, 2.5 * kf]])
+    ntri, _ = orc.measure_gridinfo(16, 1000.0, edges, [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
+    assert [int(round(v)) for v in ntri] == [120, 174, 456]
+
+
+def test_cross_routing_aab_and_abc():
+    n, box = 10, 50.0
+    kf = 2 * np.pi / box
+    edges = np.array([[0.5 * kf, 1.5 * kf], [1.5 * kf, 2.5 * kf]])
+    a, b_, c = _field(n, 1), _field(n, 2), _field(n, 5)
+    for meshes in ([a, b_], [a, b_, c]):
+        triples = np.array([[1, 0, 0], [1, 1, 0], [0, 0, 1]])
+        got = orc.measure_unnormalized(meshes, box, edges, triples)
+        for t, tr in enumerate(triples):
+            bb, _, _ = orc.brute_force_triangle(meshes, box, [edges[i] for i in tr])
+            assert abs(got[t] - bb) <= 1e-11 * abs(bb)
+    # <AAB> != <BBA>  (the two cross goldens differ)
+    x = orc.measure_unnormalized([a, b_], box, edges, [[1, 1, 0]])
+    y = orc.measure_unnormalized([b_, a], box, edges, [[1, 1, 0]])
+    assert abs(x[0] - y[0]) > 1e-6 * abs(x[0])
+
+
+def test_pk_fft_matches_direct_mode_average():
+    n, box = 12, 80.0
+    kf = 2 * np.pi / box
+    m = _field(n, 7)
+    lo, hi = 1.5 * kf, 2.5 * kf
+    p, nb, km = orc.pk_fft(m, box, lo, hi)
+    cube = orc.full_spectrum(m)
+    f = 2 * np.pi * np.fft.fftfreq(n, 1.0 / n) / box
+    kk = np.sqrt(f[:, None, None] ** 2 + f[None, :, None] ** 2 + f[None, None, :] ** 2)
+    sel = (kk >= lo) & (kk <= hi)
+    assert abs(nb - sel.sum()) < 1e-8
+    np.testing.assert_allclose(p, (np.abs(cube[sel]) ** 2).mean() * box ** 3, rtol=1e-11)
+    np.testing.assert_allclose(km, kk[sel].mean(), rtol=1e-11)
