@@ -1,0 +1,376 @@
+// Triangle contraction: sums[t] = sum_x F_r1(x) F_r2(x) F_r3(x) for a whole list of
+// triangles in ONE pass over the shell fields (sm_100a).
+//
+// Replaces the reference's per-triangle full-grid np.sum(a*b*c) loops
+// (bskit/main.py:1871-1879 for B; main.py:2024-2061 for N_tri and the three
+// k-means), which re-read three N^3 arrays per triangle.
+//
+// Design
+//  * Triangles are grouped on the host into 4x4x4 register blocks over
+//    (row1, row2, row3): a thread that owns a block keeps 64 accumulators in
+//    registers and needs only 12 field values per cell (16 pair products +
+//    64 FMAs per cell), so every shell value is read from HBM exactly once.
+//  * A persistent CTA per SM streams tiles [rows][tile_cells] of the field
+//    array through a double-buffered shared-memory ring filled by TMA bulk
+//    copies (cp.async.bulk + mbarrier complete_tx); compute on tile i overlaps
+//    the copy of tile i+1.
+//  * Per-lane rotation of the cell order makes the 128-bit shared-memory reads
+//    bank-conflict free although every lane reads different rows.
+//  * Accumulation: fp32 (or fp64 for fp64 fields) over one tile slice, then
+//    fp64 reduction (RED.ADD.F64) into a per-CTA partial row laid out
+//    [entry][block] so that a warp's 32 reductions are coalesced; a final
+//    kernel folds the per-CTA partials.  "Jobs" let one pass over a tile
+//    evaluate several row-offset variants (N_tri, k1, k2, k3 share the tile).
+#include "common.cuh"
+
+#include <algorithm>
+#include <unordered_map>
+
+namespace bsk {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  using type = float4;
+  static constexpr int W = 4;
+  __device__ static __forceinline__ void unpack(const float4& v, float (&o)[4]) {
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct Vec<double> {
+  using type = double2;
+  static constexpr int W = 2;
+  __device__ static __forceinline__ void unpack(const double2& v, double (&o)[2]) {
+    o[0] = v.x; o[1] = v.y;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
+                     const int4* __restrict__ blocks, int nblocks, int split, int njobs,
+                     const int* __restrict__ joboff, double* __restrict__ partial,
+                     int64_t partial_stride) {
+  using V = typename Vec<T>::type;
+  constexpr int W = Vec<T>::W;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // 2 mbarriers
+  T* tiles = reinterpret_cast<T*>(smem_raw + 128);
+  const size_t buf_elems = (size_t)nrows * tile_cells;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int64_t ntiles = (ncells + tile_cells - 1) / tile_cells;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int buf) {  // called by warp 0
+    const int64_t c0 = tile * tile_cells;
+    const int len = (int)min((int64_t)tile_cells, ncells - c0);
+    const uint32_t row_bytes = (uint32_t)len * sizeof(T);
+    if (lane == 0) mbar_expect_tx(&bars[buf], row_bytes * (uint32_t)nrows);
+    __syncwarp();
+    T* dst = tiles + (size_t)buf * buf_elems;
+    for (int r = lane; r < nrows; r += 32)
+      bulk_g2s(dst + (size_t)r * tile_cells, rowptr[r] + c0, row_bytes, &bars[buf]);
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles && tid < 32) issue(tile, 0);
+  uint32_t phase[2] = {0u, 0u};
+  double* my_partial = partial + (int64_t)blockIdx.x * partial_stride;
+  const int units = nblocks * split;
+  const int rowstride_v = tile_cells / W;
+
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles && tid < 32) issue(next, buf ^ 1);  // buf^1 was released by the barrier below
+    mbar_wait(&bars[buf], phase[buf]);
+    phase[buf] ^= 1u;
+
+    const int64_t c0 = tile * tile_cells;
+    const int len = (int)min((int64_t)tile_cells, ncells - c0);
+    const int nq = len / W;
+    const V* tv = reinterpret_cast<const V*>(tiles + (size_t)buf * buf_elems);
+
+    for (int u = tid; u < units; u += kThreads) {
+      const int b = u % nblocks;
+      const int g = u / nblocks;
+      const int q0 = (int)(((int64_t)nq * g) / split);
+      const int q1 = (int)(((int64_t)nq * (g + 1)) / split);
+      const int n = q1 - q0;
+      if (n <= 0) continue;
+      const int4 blk = blocks[b];
+      const int rot = lane % n;
+      for (int job = 0; job < njobs; ++job) {
+        const V* pa = tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0;
+        const V* pb = tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0;
+        const V* pc = tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0;
+        T acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = (T)0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+          int q = i + rot;
+          if (q >= n) q -= n;
+          T a[4][W], bb[4][W], c[4][W];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            Vec<T>::unpack(pa[(size_t)r * rowstride_v + q], a[r]);
+            Vec<T>::unpack(pb[(size_t)r * rowstride_v + q], bb[r]);
+            Vec<T>::unpack(pc[(size_t)r * rowstride_v + q], c[r]);
+          }
+#pragma unroll
+          for (int w = 0; w < W; ++w)
+#pragma unroll
+            for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const T pr = a[i1][w] * bb[i2][w];
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3)
+                  acc[(i1 * 4 + i2) * 4 + i3] = fma(pr, c[i3][w], acc[(i1 * 4 + i2) * 4 + i3]);
+              }
+        }
+        double* dst = my_partial + (int64_t)job * 64 * nblocks + b;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, (double)acc[e]);
+      }
+    }
+    __syncthreads();  // everyone is done with `buf` before it is refilled
+  }
+}
+
+__global__ void fold_partials_kernel(const double* __restrict__ partial, int64_t partial_stride,
+                                     int ncta, int njobs, int ntri, int nblocks,
+                                     const int* __restrict__ tri_slot, double* __restrict__ sums) {
+  const int64_t total = (int64_t)njobs * ntri;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int job = (int)(i / ntri);
+    const int t = (int)(i - (int64_t)job * ntri);
+    const double* p = partial + (int64_t)job * 64 * nblocks + tri_slot[t];
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += p[(int64_t)c * partial_stride];
+    sums[i] = s;
+  }
+}
+
+}  // namespace bsk
+
+struct bsk_cplan {
+  int ntri = 0, nrows = 0, nblocks = 0, split = 1, rounds = 1, max_jobs = 1;
+  int sm_count = 148;
+  int ncta_alloc = 0;
+  int4* d_blocks = nullptr;
+  int* d_tri_slot = nullptr;
+  double* d_partial = nullptr;
+  const void** d_rowptr = nullptr;
+  const void** h_rowptr = nullptr;  // pinned staging
+  int* d_joboff = nullptr;
+  int* h_joboff = nullptr;  // pinned staging
+  size_t smem_limit = 0;
+};
+
+using namespace bsk;
+
+template <typename T>
+static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums, cudaStream_t st) {
+  // tile size: double-buffered [nrows][tile_cells] must fit in shared memory
+  const size_t budget = std::min<size_t>(cp->smem_limit, 227 * 1024) - 1024;
+  int tile = (int)(budget / (2 * (size_t)cp->nrows * sizeof(T)));
+  tile = std::min(tile, 1024);
+  tile -= tile % 32;
+  BSK_REQUIRE(tile >= 32, "bsk_contract: %d rows do not fit in shared memory; split the row set",
+              cp->nrows);
+  const int64_t ntiles = (ncells + tile - 1) / tile;
+  const int ncta = (int)std::min<int64_t>(ntiles, cp->ncta_alloc);
+  const size_t smem = 128 + 2 * (size_t)cp->nrows * tile * sizeof(T);
+  const int64_t stride = (int64_t)njobs * 64 * cp->nblocks;
+  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
+  tile_contract_kernel<T><<<ncta, kThreads, smem, st>>>(
+      (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, cp->split,
+      njobs, cp->d_joboff, cp->d_partial, stride);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  const int64_t total = (int64_t)njobs * cp->ntri;
+  fold_partials_kernel<<<(int)std::min<int64_t>((total + 127) / 128, 148 * 8), 128, 0, st>>>(
+      cp->d_partial, stride, ncta, njobs, cp->ntri, cp->nblocks, cp->d_tri_slot, sums);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  return BSK_OK;
+}
+
+
+extern "C" {
+
+int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, int max_jobs) {
+  BSK_REQUIRE(out && rows && ntri > 0 && nrows > 0 && nrows % 4 == 0 && max_jobs >= 1,
+              "bsk_cplan_create: bad argument (ntri=%d nrows=%d, nrows must be a multiple of 4)",
+              ntri, nrows);
+  std::unordered_map<uint64_t, int> index;
+  std::vector<int4> blocks;
+  std::vector<int> slot((size_t)ntri);
+  std::vector<uint64_t> used;  // 64-bit occupancy per block, detects duplicate triangles
+  for (int t = 0; t < ntri; ++t) {
+    const int r1 = rows[3 * t], r2 = rows[3 * t + 1], r3 = rows[3 * t + 2];
+    BSK_REQUIRE(r1 >= 0 && r2 >= 0 && r3 >= 0 && r1 < nrows && r2 < nrows && r3 < nrows,
+                "bsk_cplan_create: triangle %d has a row outside [0,%d)", t, nrows);
+    const uint64_t key = ((uint64_t)(r1 >> 2) << 40) | ((uint64_t)(r2 >> 2) << 20) | (uint64_t)(r3 >> 2);
+    auto it = index.find(key);
+    int b;
+    if (it == index.end()) {
+      b = (int)blocks.size();
+      index.emplace(key, b);
+      blocks.push_back(make_int4((r1 >> 2) << 2, (r2 >> 2) << 2, (r3 >> 2) << 2, 0));
+      used.push_back(0);
+    } else {
+      b = it->second;
+    }
+    const int e = ((r1 & 3) * 4 + (r2 & 3)) * 4 + (r3 & 3);
+    BSK_REQUIRE(!((used[b] >> e) & 1ull), "bsk_cplan_create: duplicate triangle (%d,%d,%d)", r1, r2, r3);
+    used[b] |= 1ull << e;
+    slot[t] = e;  // finalised below once nblocks is known
+  }
+  bsk_cplan* cp = new bsk_cplan();
+  cp->ntri = ntri;
+  cp->nrows = nrows;
+  cp->nblocks = (int)blocks.size();
+  cp->max_jobs = max_jobs;
+  for (int t = 0; t < ntri; ++t) {
+    const int r1 = rows[3 * t], r2 = rows[3 * t + 1], r3 = rows[3 * t + 2];
+    const uint64_t key = ((uint64_t)(r1 >> 2) << 40) | ((uint64_t)(r2 >> 2) << 20) | (uint64_t)(r3 >> 2);
+    slot[t] = slot[t] * cp->nblocks + index[key];
+  }
+  // split each block's tile over `split` threads so that a round fills the CTA
+  int best = 1;
+  double best_eff = 0.0;
+  for (int g = 1; g <= 8; ++g) {
+    const int units = cp->nblocks * g;
+    const int rounds = (units + kThreads - 1) / kThreads;
+    const double eff = (double)units / ((double)rounds * kThreads);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = g;
+    }
+  }
+  cp->split = best;
+  cp->rounds = (cp->nblocks * best + kThreads - 1) / kThreads;
+
+  int dev = 0;
+  cudaDeviceProp prop;
+  BSK_CUDA(cudaGetDevice(&dev));
+  BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  cp->sm_count = prop.multiProcessorCount;
+  cp->smem_limit = prop.sharedMemPerBlockOptin;
+  cp->ncta_alloc = cp->sm_count;
+  BSK_CUDA(cudaMalloc((void**)&cp->d_blocks, sizeof(int4) * blocks.size()));
+  BSK_CUDA(cudaMemcpy(cp->d_blocks, blocks.data(), sizeof(int4) * blocks.size(), cudaMemcpyHostToDevice));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_tri_slot, sizeof(int) * (size_t)ntri));
+  BSK_CUDA(cudaMemcpy(cp->d_tri_slot, slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_partial,
+                      sizeof(double) * (size_t)cp->ncta_alloc * max_jobs * 64 * cp->nblocks));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_rowptr, sizeof(void*) * (size_t)nrows));
+  BSK_CUDA(cudaMallocHost((void**)&cp->h_rowptr, sizeof(void*) * (size_t)nrows));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_joboff, sizeof(int) * 3 * (size_t)max_jobs));
+  BSK_CUDA(cudaMallocHost((void**)&cp->h_joboff, sizeof(int) * 3 * (size_t)max_jobs));
+  *out = cp;
+  return BSK_OK;
+}
+
+int bsk_cplan_destroy(bsk_cplan* cp) {
+  if (!cp) return BSK_OK;
+  cudaFree(cp->d_blocks);
+  cudaFree(cp->d_tri_slot);
+  cudaFree(cp->d_partial);
+  cudaFree(cp->d_rowptr);
+  cudaFreeHost(cp->h_rowptr);
+  cudaFree(cp->d_joboff);
+  cudaFreeHost(cp->h_joboff);
+  delete cp;
+  return BSK_OK;
+}
+
+int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]) {
+  BSK_REQUIRE(cp && out, "bsk_cplan_info: null argument");
+  out[0] = cp->nblocks;
+  out[1] = cp->split;
+  out[2] = cp->rounds;
+  out[3] = kThreads;
+  return BSK_OK;
+}
+
+int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int64_t ncells,
+                 int njobs, const int32_t* job_off, double* sums, void* cuda_stream) {
+  BSK_REQUIRE(cp && row_ptrs && job_off && sums, "bsk_contract: null argument");
+  BSK_REQUIRE(njobs >= 1 && njobs <= cp->max_jobs, "bsk_contract: njobs=%d outside [1,%d]", njobs,
+              cp->max_jobs);
+  BSK_REQUIRE(ncells > 0 && ncells % 4 == 0, "bsk_contract: ncells must be a positive multiple of 4");
+  BSK_REQUIRE(precision == BSK_F32 || precision == BSK_F64, "bsk_contract: bad precision");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // the staging buffers are reused: wait for earlier work on this stream that may still read them
+  BSK_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < cp->nrows; ++r) {
+    BSK_REQUIRE(row_ptrs[r] && ((uintptr_t)row_ptrs[r] % 16) == 0,
+                "bsk_contract: row %d pointer is null or not 16-byte aligned", r);
+    cp->h_rowptr[r] = row_ptrs[r];
+  }
+  for (int j = 0; j < njobs; ++j)
+    for (int k = 0; k < 3; ++k) {
+      const int off = job_off[3 * j + k];
+      BSK_REQUIRE(off >= 0 && off % 4 == 0 && off < cp->nrows,
+                  "bsk_contract: job offset %d must be a multiple of 4 inside the row set", off);
+      cp->h_joboff[3 * j + k] = off;
+    }
+  BSK_CUDA(cudaMemcpyAsync(cp->d_rowptr, cp->h_rowptr, sizeof(void*) * (size_t)cp->nrows,
+                           cudaMemcpyHostToDevice, st));
+  BSK_CUDA(cudaMemcpyAsync(cp->d_joboff, cp->h_joboff, sizeof(int) * 3 * (size_t)njobs,
+                           cudaMemcpyHostToDevice, st));
+  return precision == BSK_F32 ? contract_impl<float>(cp, ncells, njobs, sums, st)
+                              : contract_impl<double>(cp, ncells, njobs, sums, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/* bskit_b200 C ABI — the drop-in boundary for the FFT-bispectrum hot path.
+ *
+ * The reference (sjforeman/bskit) has no FFI layer of its own: its hot path is
+ * Python (bskit/main.py) calling nbodykit / pmesh / pfft / mpi4py.  Each entry
+ * point below names the reference lines whose arithmetic it replaces, so a
+ * maintainer can bind it from bskit/main.py with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / numpy types cross this boundary;
+ *  - every function returns 0 (BSK_OK) or a negative code; bsk_last_error()
+ *    returns a thread-local message for the last failure;
+ *  - "device" pointers are CUDA device memory owned by the CALLER (the Python
+ *    host allocates them as torch tensors); the library only owns cuFFT plans,
+ *    small lookup tables and the contraction schedule;
+ *  - all work is enqueued on the cudaStream_t given at plan creation and is
+ *    asynchronous with respect to the host unless stated otherwise;
+ *  - a plan is not thread-safe; in a multi-GPU run every rank (one process per
+ *    GPU) makes the same calls in the same order and the host performs the
+ *    collectives (all-gather of cropped planes, all-reduce of triangle sums)
+ *    between them with torch.distributed/NCCL.
+ *
+ * Grid conventions (pmesh): cubic mesh N^3, x slowest, z contiguous; half
+ * spectrum on z; forward transform divided by N^3, inverse un-normalised;
+ * k_axis = 2*pi*fftfreq(N,1/N)/L.
+ */
+#ifndef BSKIT_B200_H
+#define BSKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSK_OK 0
+#define BSK_ERR_ARG (-1)
+#define BSK_ERR_CUDA (-2)
+#define BSK_ERR_CUFFT (-3)
+#define BSK_ERR_STATE (-4)
+
+#define BSK_F32 0
+#define BSK_F64 1
+
+/* shell kinds, bsk_shells() */
+#define BSK_KIND_DATA 0 /* delta_k * mask      main.py:1846-1861, 614-660 */
+#define BSK_KIND_UNIT 1 /* mask                number_field, main.py:280-329 */
+#define BSK_KIND_KPOW 2 /* |k|^p * mask        k_field,      main.py:227-277 */
+
+typedef struct bsk_plan bsk_plan;   /* grid geometry + cuFFT plans + k tables */
+typedef struct bsk_cplan bsk_cplan; /* triangle-list contraction schedule */
+
+typedef struct bsk_geometry {
+  int32_t nmesh;     /* N: input mesh is N^3 */
+  int32_t neval;     /* M: grid the shell fields are synthesised on. M == N
+                        reproduces the reference's transforms exactly; M < N is
+                        the band-limited evaluation (exact when M > 3*ncrop) */
+  int32_t ncrop;     /* keep modes with |n_axis| <= ncrop; >= N/2 keeps all */
+  int32_t precision; /* BSK_F32 or BSK_F64: dtype of spectra and shell fields */
+  int32_t world;     /* number of x-slab shards (ranks) */
+  int32_t rank;      /* this shard */
+  int32_t max_shells;/* largest nsh a bsk_shells() call will pass */
+  int32_t reserved;
+} bsk_geometry;
+
+/* Derived sizes, bsk_plan_info(): all counts in ELEMENTS of the plan precision
+ * (complex counts are numbers of complex values). */
+typedef struct bsk_info {
+  int64_t kx, ky, kz;          /* cropped spectrum cube dims */
+  int64_t nx0, nxl;            /* local x-planes of the N grid  [nx0, nx0+nxl) */
+  int64_t mx0, mxl;            /* local x-planes of the M grid */
+  int64_t fwd_work_complex;    /* nxl * N * (N/2+1) */
+  int64_t planes_local_complex;/* nxl * ky * kz */
+  int64_t planes_all_complex;  /* N * ky * kz */
+  int64_t cube_complex;        /* kx * ky * kz */
+  int64_t xcols_complex_per_shell;  /* M * ky * kz       (W buffer) */
+  int64_t planes2d_complex_per_shell;/* mxl * M * (M/2+1) (P buffer) */
+  int64_t field_real_per_shell;     /* mxl * M * M = local cells */
+  int64_t fft_work_bytes;      /* cuFFT work areas owned by the plan */
+} bsk_info;
+
+int bsk_version(void);
+const char* bsk_last_error(void);
+
+/* Plan.  kx_tab/ky_tab/kz_tab: HOST float64 wavenumber per cropped-cube index
+ * along each axis, computed by the host exactly as the reference's grid does
+ * (2*pi*fftfreq(N,1/N)/L, negative frequencies in the upper half), so that the
+ * in-kernel |k| = sqrt(kx^2+ky^2+kz^2) is bit-identical to numpy's
+ * (main.py:1850).  comp_x/y/z: optional HOST float64 multiplicative
+ * compensation per cropped-cube index (CIC window, measure_bs_fast.py:45-57);
+ * NULL = none. */
+int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_tab,
+                    const double* ky_tab, const double* kz_tab, void* cuda_stream);
+int bsk_plan_destroy(bsk_plan* plan);
+int bsk_plan_info(const bsk_plan* plan, bsk_info* out);
+int bsk_set_compensation(bsk_plan* plan, const double* comp_x, const double* comp_y,
+                         const double* comp_z);
+
+/* Forward transform of this rank's x-slab (replaces mesh.paint(mode='complex'),
+ * main.py:1608-1621, plus the queued compensation action).
+ *   mesh_slab    device, [nxl][N][N] real, dtype mesh_dtype (BSK_F32/BSK_F64);
+ *                converted to the plan precision if it differs
+ *   work         device, fwd_work_complex complex values (+ nxl*N*N reals when a
+ *                dtype conversion is needed: pass work2)
+ *   planes_local device out, [nxl][ky][kz] complex: 2-D r2c over (y,z), scaled by
+ *                1/N^3, y/z compensation applied, cropped to the kept modes */
+int bsk_forward_local(bsk_plan* plan, const void* mesh_slab, int mesh_dtype, void* work,
+                      void* convert_work, void* planes_local);
+/* After the host all-gathered planes_local into planes_all [N][ky][kz]:
+ * in-place x transform and crop -> cube [kx][ky][kz] (x compensation applied). */
+int bsk_forward_finish(bsk_plan* plan, void* planes_all, void* cube);
+
+/* Exact integer number of full-cube modes in each k-bin (inclusive both ends,
+ * main.py:1852), Hermitian multiplicity included.  lo/hi: HOST float64[nbins];
+ * counts: HOST out int64[nbins].  Synchronous. */
+int bsk_modes_per_bin(bsk_plan* plan, int nbins, const double* lo, const double* hi,
+                      int64_t* counts);
+
+/* Shell synthesis for nsh k-bins (replaces the per-bin mask + c2r of
+ * main.py:1846-1861 / number_field / k_field): k-shell filter of the cube,
+ * inverse x transform, scatter into zero-padded (y,z) half-spectra of the local
+ * planes, batched 2-D c2r.
+ *   cube     device [kx][ky][kz] complex (ignored for UNIT / KPOW kinds)
+ *   lo, hi   HOST float64[nsh] bin edges, both inclusive
+ *   xcols    device scratch, nsh * xcols_complex_per_shell complex
+ *   planes2d device scratch, nsh * planes2d_complex_per_shell complex
+ *   fields   device out, [nsh][mxl*M*M] real (contiguous) */
+int bsk_shells(bsk_plan* plan, const void* cube, int kind, double kpow, int nsh,
+               const double* lo, const double* hi, void* xcols, void* planes2d, void* fields);
+
+/* Triangle contraction schedule for a list of triangles given as TILE-ROW
+ * triples: rows[t] = (r1, r2, r3) indexes the array of field pointers handed to
+ * bsk_contract().  Triangles are grouped into 4x4x4 register blocks. */
+int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, int max_jobs);
+int bsk_cplan_destroy(bsk_cplan* cp);
+int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, rounds, threads */
+
+/* sums[j][t] = sum over local cells x of
+ *     F[r1 + off[j][0]](x) * F[r2 + off[j][1]](x) * F[r3 + off[j][2]](x)
+ * (replaces the per-triangle np.sum of main.py:1875, 2027-2055; the caller
+ * applies V^2/N^3 etc. and all-reduces across ranks).
+ *   row_ptrs  HOST array of nrows DEVICE pointers, one real field of ncells each
+ *   job_off   HOST int32[njobs][3] row offsets per job (0,0,0 for plain B)
+ *   sums      device out float64 [njobs][ntri]; fp64 accumulation throughout */
+int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int64_t ncells,
+                 int njobs, const int32_t* job_off, double* sums, void* cuda_stream);
+
+/* number of kernels this library has launched since load (bench bookkeeping) */
+int64_t bsk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSKIT_B200_H */

@@ -1,0 +1,285 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 CPU oracle
+on identical seeded meshes.  Tolerances follow BASELINE.json's north_star:
+bin assignment / mode counts bit-exact, B and normalisation within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bskit_oracle as orc
+from conftest import REF_OUT, fmt_e
+
+pytestmark = pytest.mark.gpu
+
+RTOL_B = 1e-5          # north_star tolerance for floating-point results
+
+
+@pytest.fixture(scope="module")
+def bk():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import bskit_b200
+    from bskit_b200 import _native
+    _native.lib()                       # fail loudly if the extension is not built
+    return bskit_b200
+
+
+@pytest.fixture(scope="module")
+def syn():
+    from bskit_b200 import synthetic
+    return synthetic
+
+
+def assert_b_close(got, want, rtol=RTOL_B):
+    """Per-triangle relative error where B is not accidentally ~0, and an absolute
+    bound tied to the largest |B| everywhere (the sums cancel to ~0 for some bins)."""
+    got, want = np.asarray(got), np.asarray(want)
+    scale = np.abs(want).max()
+    big = np.abs(want) > 1e-3 * scale
+    rel = np.abs(got[big] - want[big]) / np.abs(want[big])
+    assert rel.max() < rtol, f"max relative error {rel.max():.3e}"
+    assert np.abs(got - want).max() < rtol * 1e-1 * scale + 0.0, \
+        f"max abs error / max|B| = {np.abs(got - want).max() / scale:.3e}"
+
+
+# --- C1: 64^3 Gaussian mesh, equilateral bins, auto-bispectrum ---------------------- #
+@pytest.mark.parametrize("grid", ["full", "auto"])
+def test_c1_equilateral_64(bk, syn, grid):
+    n, nb = 64, 20
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.gaussian_mesh(n, seed=1)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk,
+                          triangle_type="equilateral", grid=grid)
+    assert len(fb.k_edges) == nb
+    got = fb.measure_bispectrum_faster(0, nb)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_equilateral(edges)
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
+    assert np.array_equal(got["index"], np.arange(nb))
+    assert np.array_equal(got["k_edge"], np.hstack((edges, edges, edges)))
+    assert_b_close(got["B"], want)
+    fb.close()
+
+
+# --- all triangles, auto + normalisation, both grids, both precisions ----------------- #
+@pytest.mark.parametrize("grid,dtype", [("full", np.float32), ("auto", np.float32),
+                                        ("full", np.float64), ("auto", np.float64)])
+def test_all_triangles_64(bk, syn, grid, dtype):
+    n, nb = 64, 12
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.lognormal_mesh(n, seed=1, dtype=dtype)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid=grid)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    e6, idx = orc.triangles_all(edges, 1)
+    assert np.array_equal(fb.k_edges, e6) and np.array_equal(fb.k_indices, idx)
+    got = fb.measure_bispectrum_faster(0, len(idx))
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
+    assert_b_close(got["B"], want, RTOL_B if dtype == np.float32 else 1e-10)
+    gi = fb.measure_gridinfo_faster(0, len(idx))
+    wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx, workers=4)
+    assert np.array_equal(gi["N_tri"], np.rint(wn))
+    assert np.abs(wn - np.rint(wn)).max() < 1e-4          # the oracle's counts are integers too
+    np.testing.assert_allclose(gi["k_mean"], wk, rtol=1e-10)
+    fb.close()
+
+
+def test_aliased_regime_matches_oracle(bk, syn):
+    """3*n_max >= N: triangles close modulo N; the engine must keep the mesh's own grid
+    (no band-limited evaluation) and reproduce the wrapped counts."""
+    n, nb = 32, 12                      # n_max ~ 13 > 32/3
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.lognormal_mesh(n, seed=3, dtype=np.float64)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="auto")
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    got = fb.measure_bispectrum_faster(0, len(idx))
+    gi = fb.measure_gridinfo_faster(0, len(idx))
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx)
+    wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx)
+    assert_b_close(got["B"], want, 1e-10)
+    assert np.array_equal(gi["N_tri"], np.rint(wn))
+    fb.close()
+
+
+def test_full_spectrum_regime(bk, syn):
+    """Bins reaching the Nyquist frequency: nothing can be cropped."""
+    n = 16
+    kf = syn.KF
+    mesh = syn.lognormal_mesh(n, seed=4, dtype=np.float64)
+    kmin, kmax, dk = 0.5 * kf, 0.5 * kf + 14.5 * kf, kf
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk,
+                          triangle_type="equilateral")
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_equilateral(edges)
+    got = fb.measure_bispectrum_faster(0, len(idx))
+    gi = fb.measure_gridinfo_faster(0, len(idx))
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx)
+    wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx)
+    assert_b_close(got["B"], want, 1e-10)
+    assert np.array_equal(gi["N_tri"], np.rint(wn))
+    ok = wn > 0.5
+    np.testing.assert_allclose(gi["k_mean"][ok], wk[ok], rtol=1e-10)
+    assert np.isnan(gi["k_mean"][~ok]).all()
+    fb.close()
+
+
+# --- golden grid-info file of the reference ------------------------------------------- #
+def test_gridinfo_golden_file_byte_for_byte(bk, tmp_path):
+    """examples/tests/scripts/test_compute_bs_gridinfo.sh -> Lbox1000_512_kf_3kf_3lowkbins.dat.
+    N_tri and k_mean do not depend on the mesh values or (while 3 n_max < N) on N."""
+    n = 64
+    mesh = np.zeros((n, n, n), dtype=np.float32)
+    fb = bk.FFTBispectrum(mesh, BoxSize=np.ones(3) * 1000.0, dk=0.00628, kmin=0.00314, kmax=0.1,
+                          num_lowk_bins=3, dk_high=0.01884, triangle_type="all",
+                          for_grid_info_only=True)
+    out = tmp_path / "gridinfo.dat"
+    fb.measure_gridinfo_faster(imin=0, imax=200, out_file=str(out))
+    got = out.read_text().strip().splitlines()
+    want = open(os.path.join(REF_OUT, "Lbox1000_512_kf_3kf_3lowkbins.dat")).read().strip().splitlines()
+    assert got == want
+    # the slow entry point gives the same file (the reference's two goldens are identical)
+    out2 = tmp_path / "gridinfo_slow.dat"
+    fb2 = bk.FFTBispectrum(mesh, BoxSize=np.ones(3) * 1000.0, dk=0.00628, kmin=0.00314, kmax=0.1,
+                           num_lowk_bins=3, dk_high=0.01884, for_grid_info_only=True)
+    fb2.measure_bispectrum(0, 200, out_file=str(out2), meas_type="grid_info")
+    assert out2.read_text().strip().splitlines() == want
+    fb.close()
+    fb2.close()
+
+
+def test_mode_counts_bit_exact(bk, syn):
+    from bskit_b200 import engine as eng, _native as nat
+    import torch
+    n = 48
+    kmin, kmax, dk = syn.bench_bins(14)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    edges = np.vstack((edges, [[2 * syn.KF, 3 * syn.KF]]))      # edges that sit exactly on modes
+    g = eng.choose_grid(n, syn.BOX, edges[:, 1].max(), "full")
+    e = eng.Engine(g, syn.BOX, nat.F64, device=torch.device("cuda", 0))
+    got = e.backend.modes_per_bin(edges[:, 0], edges[:, 1])
+    assert np.array_equal(got, orc.modes_per_bin(n, syn.BOX, edges))
+    e.close()
+
+
+# --- cross bispectra ------------------------------------------------------------------ #
+@pytest.mark.parametrize("nfields", [2, 3])
+def test_cross_bispectrum_routing(bk, syn, nfields):
+    n, nb = 48, 8
+    kmin, kmax, dk = syn.bench_bins(nb)
+    a = syn.lognormal_mesh(n, seed=1)
+    b = syn.baryon_like_mesh(a, seed=2)
+    c = syn.lognormal_mesh(n, seed=5)
+    meshes = [a, b, c][:nfields]
+    fb = bk.FFTBispectrum(a, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, second=b,
+                          third=c if nfields == 3 else None, grid="full")
+    edges = orc.bin_edges(kmin, kmax, dk)
+    e6, idx = orc.triangles_all(edges, nfields)
+    assert np.array_equal(fb.k_indices, idx) and np.array_equal(fb.k_edges, e6)
+    got = fb.measure_bispectrum_faster(0, len(idx))
+    want = orc.measure_unnormalized(meshes, syn.BOX, edges, idx, workers=4)
+    assert_b_close(got["B"], want)
+    fb.close()
+
+
+def test_isosceles_and_squeezed_cross(bk, syn):
+    """C3 in miniature: isosceles m=2 and squeezed bins, <AAB>."""
+    n, nb = 64, 18
+    kmin, kmax, dk = syn.bench_bins(nb)
+    a = syn.lognormal_mesh(n, seed=1)
+    b = syn.baryon_like_mesh(a, seed=2)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    for kw, (e6, idx) in ((dict(triangle_type="isosceles", isos_mult=2.0), orc.triangles_isosceles(edges, 2.0)),
+                          (dict(triangle_type="squeezed", squeezed_bin_index=0), orc.triangles_squeezed(edges, 0))):
+        fb = bk.FFTBispectrum(a, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, second=b, **kw)
+        assert np.array_equal(fb.k_indices, idx)
+        got = fb.measure_bispectrum_faster(0, len(idx))
+        want = orc.measure_unnormalized([a, b], syn.BOX, edges, idx, workers=4)
+        assert_b_close(got["B"], want)
+        fb.close()
+
+
+def test_cic_compensation(bk, syn):
+    n, nb = 48, 8
+    kmin, kmax, dk = syn.bench_bins(nb)
+    a = syn.lognormal_mesh(n, seed=1, dtype=np.float64)
+    src = bk.ArrayMesh(a, syn.BOX).apply(bk.CompensateCIC(n), kind="circular", mode="complex")
+    fb = bk.FFTBispectrum(src, kmin=kmin, kmax=kmax, dk=dk, triangle_type="equilateral")
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_equilateral(edges)
+    got = fb.measure_bispectrum_faster(0, nb)
+    want = orc.measure_unnormalized([a], syn.BOX, edges, idx, nmesh_cic=n)
+    plain = orc.measure_unnormalized([a], syn.BOX, edges, idx)
+    assert_b_close(got["B"], want, 1e-10)
+    assert np.abs(want - plain).max() > 1e-3 * np.abs(want).max()     # the compensation matters
+    fb.close()
+
+
+# --- slow-path API, units, module functions ------------------------------------------- #
+def test_measure_bispectrum_full_and_units(bk, syn, tmp_path):
+    n, nb = 48, 6
+    kmin, kmax, dk = syn.bench_bins(nb)
+    a = syn.lognormal_mesh(n, seed=1, dtype=np.float64)
+    u = 2.0
+    fb = bk.FFTBispectrum(a, BoxSize=syn.BOX, kmin=kmin / u, kmax=kmax / u, dk=dk / u,
+                          pos_units_mpcoverh=u)
+    out = tmp_path / "full.dat"
+    got = fb.measure_bispectrum(2, 9, out_file=str(out), meas_type="full")
+    e6 = fb.k_edges[2:9]
+    edges, triples = np.unique((e6 * u).reshape(-1, 2), axis=0, return_inverse=True)
+    triples = np.asarray(triples).reshape(-1, 3)
+    wb = orc.measure_unnormalized([a], syn.BOX, edges, triples, pos_units=u)
+    wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, triples, pos_units=u)
+    assert np.array_equal(got["index"], np.arange(2, 9))
+    assert np.array_equal(got["N_tri"], np.rint(wn))
+    np.testing.assert_allclose(got["k_mean"], wk, rtol=1e-10)
+    np.testing.assert_allclose(got["B"], wb / wn, rtol=1e-9)
+    rows = np.loadtxt(out)
+    assert rows.shape == (7, 12)
+    assert fmt_e(rows[0, 10]) == fmt_e(got["B"][0])
+    fb.close()
+
+
+def test_module_functions(bk, syn):
+    n = 32
+    a = syn.lognormal_mesh(n, seed=2, dtype=np.float64)
+    box3 = np.ones(3) * syn.BOX
+    n3 = np.array([n, n, n])
+    lo, hi = 1.5 * syn.KF, 3.5 * syn.KF
+    nf = bk.number_field(box3, n3, lo, hi)
+    kfld = bk.k_field(box3, n3, lo, hi, 1.0)
+    np.testing.assert_allclose(nf, orc.number_field(n, syn.BOX, lo, hi), atol=1e-9)
+    np.testing.assert_allclose(kfld, orc.k_field(n, syn.BOX, lo, hi, 1.0), atol=1e-10)
+    p, nbin, km = bk.pk_FFT(bk.ArrayMesh(a, syn.BOX), lo, hi)
+    wp, wn, wk = orc.pk_fft(a, syn.BOX, lo, hi)
+    np.testing.assert_allclose([p, nbin, km], [wp, wn, wk], rtol=1e-10)
+    bins = [(lo, hi), (0.5 * syn.KF, 1.5 * syn.KF), (0.5 * syn.KF, 1.5 * syn.KF)]
+    B, N, k1, k2, k3 = bk.bk_FFT_full(bk.ArrayMesh(a, syn.BOX), *bins)
+    edges, tr = np.unique(np.array(bins), axis=0, return_inverse=True)
+    tr = np.asarray(tr).reshape(1, 3)
+    wn2, wk2 = orc.measure_gridinfo(n, syn.BOX, edges, tr)
+    wb = orc.measure_unnormalized([a], syn.BOX, edges, tr)
+    assert N == round(wn2[0])
+    np.testing.assert_allclose([k1, k2, k3], wk2[0], rtol=1e-10)
+    np.testing.assert_allclose(B, wb[0] / wn2[0], rtol=1e-9)
+
+
+def test_band_limited_grid_equals_full_grid_256(bk, syn):
+    """Size-independent property at a size the oracle cannot sweep quickly: the exact
+    band-limited evaluation (grid='auto') and the mesh's own grid (grid='full') agree."""
+    n, nb = 256, 24
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.lognormal_mesh(n, seed=1)
+    res = {}
+    for grid in ("full", "auto"):
+        fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid=grid)
+        res[grid] = fb.measure_bispectrum_faster(0, 10 ** 9)["B"]
+        fb.close()
+    assert_b_close(res["auto"], res["full"])
+    # spot-check 6 triangles against the oracle at full size
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    pick = np.linspace(0, len(idx) - 1, 6).astype(int)
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx[pick], workers=8)
+    rel = np.abs(res["full"][pick] - want) / np.abs(want)
+    assert rel.max() < RTOL_B, rel
