@@ -27,12 +27,12 @@ EXPORTS = (
 
 class Geometry(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "reserved")]
+                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "fft_precision")]
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
-                ("kx", "ky", "kz", "nx0", "nxl", "mx0", "mxl", "fwd_work_complex",
+                ("kx", "ky", "kz", "nx0", "nxl", "mx0", "mxl", "fwd_batch", "fwd_work_complex",
                  "planes_local_complex", "planes_all_complex", "cube_complex",
                  "xcols_complex_per_shell", "planes2d_complex_per_shell", "field_real_per_shell",
                  "fft_work_bytes")]
@@ -70,7 +70,7 @@ def lib():
     L.bsk_cplan_create.argtypes = [C.POINTER(vp), ip, C.POINTER(C.c_int32), ip, ip]
     L.bsk_cplan_destroy.argtypes = [vp]
     L.bsk_cplan_info.argtypes = [vp, C.POINTER(C.c_int64)]
-    L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
+    L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -68,19 +68,22 @@ template <typename T> struct Vec;
 template <> struct Vec<float> {
   using type = float4;
   static constexpr int W = 4;
-  __device__ static __forceinline__ void unpack(const float4& v, float (&o)[4]) {
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  template <typename TC>
+  __device__ static __forceinline__ void unpack(const float4& v, TC (&o)[4]) {
+    o[0] = (TC)v.x; o[1] = (TC)v.y; o[2] = (TC)v.z; o[3] = (TC)v.w;
   }
 };
 template <> struct Vec<double> {
   using type = double2;
   static constexpr int W = 2;
-  __device__ static __forceinline__ void unpack(const double2& v, double (&o)[2]) {
-    o[0] = v.x; o[1] = v.y;
+  template <typename TC>
+  __device__ static __forceinline__ void unpack(const double2& v, TC (&o)[2]) {
+    o[0] = (TC)v.x; o[1] = (TC)v.y;
   }
 };
 
-template <typename T>
+// T: storage type of the fields; TC: type of the products and per-tile accumulators
+template <typename T, typename TC>
 __global__ void __launch_bounds__(kThreads, 1)
 tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
                      const int4* __restrict__ blocks, int nblocks, int split, int njobs,
@@ -147,14 +150,14 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
         const V* pa = tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0;
         const V* pb = tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0;
         const V* pc = tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0;
-        T acc[64];
+        TC acc[64];
 #pragma unroll
-        for (int e = 0; e < 64; ++e) acc[e] = (T)0;
+        for (int e = 0; e < 64; ++e) acc[e] = (TC)0;
 #pragma unroll 1
         for (int i = 0; i < n; ++i) {
           int q = i + rot;
           if (q >= n) q -= n;
-          T a[4][W], bb[4][W], c[4][W];
+          TC a[4][W], bb[4][W], c[4][W];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             Vec<T>::unpack(pa[(size_t)r * rowstride_v + q], a[r]);
@@ -167,7 +170,7 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
             for (int i1 = 0; i1 < 4; ++i1)
 #pragma unroll
               for (int i2 = 0; i2 < 4; ++i2) {
-                const T pr = a[i1][w] * bb[i2][w];
+                const TC pr = a[i1][w] * bb[i2][w];
 #pragma unroll
                 for (int i3 = 0; i3 < 4; ++i3)
                   acc[(i1 * 4 + i2) * 4 + i3] = fma(pr, c[i3][w], acc[(i1 * 4 + i2) * 4 + i3]);
@@ -215,7 +218,7 @@ struct bsk_cplan {
 
 using namespace bsk;
 
-template <typename T>
+template <typename T, typename TC>
 static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums, cudaStream_t st) {
   // tile size: double-buffered [nrows][tile_cells] must fit in shared memory
   const size_t budget = std::min<size_t>(cp->smem_limit, 227 * 1024) - 1024;
@@ -228,10 +231,10 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   const int ncta = (int)std::min<int64_t>(ntiles, cp->ncta_alloc);
   const size_t smem = 128 + 2 * (size_t)cp->nrows * tile * sizeof(T);
   const int64_t stride = (int64_t)njobs * 64 * cp->nblocks;
-  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
+  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T, TC>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
-  tile_contract_kernel<T><<<ncta, kThreads, smem, st>>>(
+  tile_contract_kernel<T, TC><<<ncta, kThreads, smem, st>>>(
       (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, cp->split,
       njobs, cp->d_joboff, cp->d_partial, stride);
   count_launch();
@@ -343,13 +346,16 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]) {
   return BSK_OK;
 }
 
-int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int64_t ncells,
-                 int njobs, const int32_t* job_off, double* sums, void* cuda_stream) {
+int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int accum_precision,
+                 int64_t ncells, int njobs, const int32_t* job_off, double* sums,
+                 void* cuda_stream) {
   BSK_REQUIRE(cp && row_ptrs && job_off && sums, "bsk_contract: null argument");
   BSK_REQUIRE(njobs >= 1 && njobs <= cp->max_jobs, "bsk_contract: njobs=%d outside [1,%d]", njobs,
               cp->max_jobs);
   BSK_REQUIRE(ncells > 0 && ncells % 4 == 0, "bsk_contract: ncells must be a positive multiple of 4");
   BSK_REQUIRE(precision == BSK_F32 || precision == BSK_F64, "bsk_contract: bad precision");
+  BSK_REQUIRE(accum_precision == BSK_F64 || accum_precision == precision,
+              "bsk_contract: accum_precision must be F64 or equal to precision");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   // the staging buffers are reused: wait for earlier work on this stream that may still read them
   BSK_CUDA(cudaStreamSynchronize(st));
@@ -369,8 +375,9 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int6
                            cudaMemcpyHostToDevice, st));
   BSK_CUDA(cudaMemcpyAsync(cp->d_joboff, cp->h_joboff, sizeof(int) * 3 * (size_t)njobs,
                            cudaMemcpyHostToDevice, st));
-  return precision == BSK_F32 ? contract_impl<float>(cp, ncells, njobs, sums, st)
-                              : contract_impl<double>(cp, ncells, njobs, sums, st);
+  if (precision == BSK_F64) return contract_impl<double, double>(cp, ncells, njobs, sums, st);
+  return accum_precision == BSK_F64 ? contract_impl<float, double>(cp, ncells, njobs, sums, st)
+                                    : contract_impl<float, float>(cp, ncells, njobs, sums, st);
 }
 
 }  // extern "C"

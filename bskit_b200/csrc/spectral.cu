@@ -106,7 +106,7 @@ __device__ __forceinline__ double knorm_exact(double kx, double ky, double kz) {
 }
 
 template <typename T>
-__global__ void shell_filter_kernel(const typename Cx<T>::type* __restrict__ cube,  // [Kx][Ky][Kz]
+__global__ void shell_filter_kernel(const double2* __restrict__ cube,  // [Kx][Ky][Kz] float64
                                     typename Cx<T>::type* __restrict__ xcols,  // [M][nsh][Ky][Kz]
                                     int Kx, int Ky, int Kz, int N, int M, int nsh, int kind,
                                     double kpow, BinEdges bins, const double* __restrict__ kxt,
@@ -123,7 +123,9 @@ __global__ void shell_filter_kernel(const typename Cx<T>::type* __restrict__ cub
     double kk = knorm_exact(kxt[jx], kyt[jy], kzt[jz]);
     typename Cx<T>::type v;
     if (kind == BSK_KIND_DATA) {
-      v = cube[i];
+      const double2 c = cube[i];
+      v.x = (T)c.x;
+      v.y = (T)c.y;
     } else if (kind == BSK_KIND_UNIT) {
       v.x = (T)1;
       v.y = (T)0;
@@ -236,7 +238,7 @@ static int get_invx(bsk_plan* p, int nsh, cufftHandle* out) {
   long long emb[1] = {M};
   cufftHandle h;
   int rc = make_plan_many(&h, 1, n, emb, cols, 1, emb, cols, 1,
-                          p->g.precision == BSK_F32 ? CUFFT_C2C : CUFFT_Z2Z, cols, p->stream,
+                          p->g.fft_precision == BSK_F32 ? CUFFT_C2C : CUFFT_Z2Z, cols, p->stream,
                           &p->fft_work_bytes);
   if (rc) return rc;
   p->invx[nsh] = h;
@@ -253,10 +255,14 @@ static int get_inv2d(bsk_plan* p, int nsh, cufftHandle* out) {
   int M = p->g.neval;
   long long n[2] = {M, M};
   long long inembed[2] = {M, M / 2 + 1};
-  long long onembed[2] = {M, M};
+  // same precision for transform and storage: out of place into the compact field array;
+  // float64 transform with float32 storage: in place (rows padded to M+2 reals), narrowed after
+  const bool inplace = p->g.fft_precision != p->g.precision;
+  long long onembed[2] = {M, inplace ? M + 2 : M};
   cufftHandle h;
-  int rc = make_plan_many(&h, 2, n, inembed, 1, (long long)M * (M / 2 + 1), onembed, 1, (long long)M * M,
-                          p->g.precision == BSK_F32 ? CUFFT_C2R : CUFFT_Z2D,
+  int rc = make_plan_many(&h, 2, n, inembed, 1, (long long)M * (M / 2 + 1), onembed, 1,
+                          inplace ? (long long)M * (M + 2) : (long long)M * M,
+                          p->g.fft_precision == BSK_F32 ? CUFFT_C2R : CUFFT_Z2D,
                           (long long)nsh * p->info.mxl, p->stream, &p->fft_work_bytes);
   if (rc) return rc;
   p->inv2d[nsh] = h;
@@ -268,17 +274,30 @@ static int get_inv2d(bsk_plan* p, int nsh, cufftHandle* out) {
 
 using namespace bsk;
 
-template <typename T>
+// float64 rows padded to M+2 (in-place c2r output) -> compact float32 field rows
+__global__ void narrow_rows_kernel(const double* __restrict__ src, float* __restrict__ dst,
+                                   int64_t rows, int M) {
+  const int64_t total = rows * (M / 2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (M / 2);
+    const int c = (int)(i - r * (M / 2));
+    const double2 v = reinterpret_cast<const double2*>(src + r * (M + 2))[c];
+    reinterpret_cast<float2*>(dst + r * M)[c] = make_float2((float)v.x, (float)v.y);
+  }
+}
+
+template <typename TF, typename TS>  // transform precision, storage precision
 static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int nsh,
                        const BinEdges& be, void* xcols, void* planes2d, void* fields) {
-  using C = typename Cx<T>::type;
+  using C = typename Cx<TF>::type;
   const bsk_info& f = p->info;
   const int N = p->g.nmesh, M = p->g.neval;
   const int64_t xc = (int64_t)nsh * f.xcols_complex_per_shell;
   if (f.kx != M)  // rows of the padded x axis that no kept mode maps to must be zero
     BSK_CUDA(cudaMemsetAsync(xcols, 0, sizeof(C) * (size_t)xc, p->stream));
-  shell_filter_kernel<T><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-      (const C*)cube, (C*)xcols, (int)f.kx, (int)f.ky, (int)f.kz, N, M, nsh, kind, kpow, be,
+  shell_filter_kernel<TF><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
+      (const double2*)cube, (C*)xcols, (int)f.kx, (int)f.ky, (int)f.kz, N, M, nsh, kind, kpow, be,
       p->d_kx, p->d_ky, p->d_kz);
   count_launch();
   BSK_CUDA(cudaGetLastError());
@@ -286,20 +305,28 @@ static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int
   int rc;
   if ((rc = get_invx(p, nsh, &hx))) return rc;
   if ((rc = get_inv2d(p, nsh, &h2))) return rc;
-  if (sizeof(T) == 4)
+  if (sizeof(TF) == 4)
     BSK_FFT(cufftExecC2C(hx, (cufftComplex*)xcols, (cufftComplex*)xcols, CUFFT_INVERSE));
   else
     BSK_FFT(cufftExecZ2Z(hx, (cufftDoubleComplex*)xcols, (cufftDoubleComplex*)xcols, CUFFT_INVERSE));
   const int64_t rows = (int64_t)nsh * f.mxl * M;
   int grid = (int)(rows < 148 * 32 ? rows : 148 * 32);
-  scatter_planes_kernel<T><<<grid, 128, 0, p->stream>>>((const C*)xcols, (C*)planes2d, M, (int)f.ky,
-                                                        (int)f.kz, nsh, (int)f.mx0, (int)f.mxl);
+  scatter_planes_kernel<TF><<<grid, 128, 0, p->stream>>>((const C*)xcols, (C*)planes2d, M, (int)f.ky,
+                                                         (int)f.kz, nsh, (int)f.mx0, (int)f.mxl);
   count_launch();
   BSK_CUDA(cudaGetLastError());
-  if (sizeof(T) == 4)
-    BSK_FFT(cufftExecC2R(h2, (cufftComplex*)planes2d, (cufftReal*)fields));
-  else
-    BSK_FFT(cufftExecZ2D(h2, (cufftDoubleComplex*)planes2d, (cufftDoubleReal*)fields));
+  if (sizeof(TF) == sizeof(TS)) {
+    if (sizeof(TF) == 4)
+      BSK_FFT(cufftExecC2R(h2, (cufftComplex*)planes2d, (cufftReal*)fields));
+    else
+      BSK_FFT(cufftExecZ2D(h2, (cufftDoubleComplex*)planes2d, (cufftDoubleReal*)fields));
+  } else {
+    BSK_FFT(cufftExecZ2D(h2, (cufftDoubleComplex*)planes2d, (cufftDoubleReal*)planes2d));
+    narrow_rows_kernel<<<grid_for(rows * (M / 2), 256), 256, 0, p->stream>>>(
+        (const double*)planes2d, (float*)fields, rows, M);
+    count_launch();
+    BSK_CUDA(cudaGetLastError());
+  }
   return BSK_OK;
 }
 
@@ -328,6 +355,9 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   BSK_REQUIRE(N >= 4 && N % 2 == 0, "nmesh must be even and >= 4 (got %d)", N);
   BSK_REQUIRE(M >= 4 && M % 2 == 0 && M <= N, "neval must be even, >= 4 and <= nmesh (got %d)", M);
   BSK_REQUIRE(g.precision == BSK_F32 || g.precision == BSK_F64, "bad precision %d", g.precision);
+  BSK_REQUIRE(g.fft_precision == BSK_F32 || g.fft_precision == BSK_F64, "bad fft_precision %d",
+              g.fft_precision);
+  BSK_REQUIRE(g.fft_precision >= g.precision, "fft_precision may not be lower than precision");
   BSK_REQUIRE(g.world >= 1 && g.rank >= 0 && g.rank < g.world, "bad world/rank %d/%d", g.world,
               g.rank);
   BSK_REQUIRE(N % g.world == 0 && M % g.world == 0,
@@ -348,7 +378,13 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   f.nx0 = f.nxl * g.rank;
   f.mxl = M / g.world;
   f.mx0 = f.mxl * g.rank;
-  f.fwd_work_complex = f.nxl * (int64_t)N * (N / 2 + 1);
+  // the forward transform runs in float64 whatever the shell precision (a float32 FFT's error
+  // is relative to the whole spectrum's rms and would swamp the weak high-k modes); it is
+  // chunked over planes so that its work buffers stay below ~1 GiB
+  f.fwd_batch = 1;
+  for (int64_t b = 1; b <= f.nxl; ++b)
+    if (f.nxl % b == 0 && b * (int64_t)N * (N / 2 + 1) * 16 <= (1ll << 30)) f.fwd_batch = b;
+  f.fwd_work_complex = f.fwd_batch * (int64_t)N * (N / 2 + 1);
   f.planes_local_complex = f.nxl * f.ky * f.kz;
   f.planes_all_complex = (int64_t)N * f.ky * f.kz;
   f.cube_complex = f.kx * f.ky * f.kz;
@@ -365,13 +401,12 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   if ((rc = upload(&p->d_cy, ones.data(), f.ky, p->stream))) return rc;
   if ((rc = upload(&p->d_cz, ones.data(), f.kz, p->stream))) return rc;
 
-  const bool sp = g.precision == BSK_F32;
-  {  // forward: batched 2-D real-to-complex over the local planes
+  {  // forward: batched 2-D real-to-complex over chunks of the local planes (float64)
     long long n[2] = {N, N};
     long long inembed[2] = {N, N};
     long long onembed[2] = {N, N / 2 + 1};
     rc = make_plan_many(&p->fwd2d, 2, n, inembed, 1, (long long)N * N, onembed, 1,
-                        (long long)N * (N / 2 + 1), sp ? CUFFT_R2C : CUFFT_D2Z, f.nxl, p->stream,
+                        (long long)N * (N / 2 + 1), CUFFT_D2Z, f.fwd_batch, p->stream,
                         &p->fft_work_bytes);
     if (rc) return rc;
   }
@@ -379,8 +414,8 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
     long long cols = f.ky * f.kz;
     long long n[1] = {N};
     long long emb[1] = {N};
-    rc = make_plan_many(&p->fwdx, 1, n, emb, cols, 1, emb, cols, 1, sp ? CUFFT_C2C : CUFFT_Z2Z,
-                        cols, p->stream, &p->fft_work_bytes);
+    rc = make_plan_many(&p->fwdx, 1, n, emb, cols, 1, emb, cols, 1, CUFFT_Z2Z, cols, p->stream,
+                        &p->fft_work_bytes);
     if (rc) return rc;
   }
   f.fft_work_bytes = (int64_t)p->fft_work_bytes;
@@ -429,37 +464,31 @@ int bsk_forward_local(bsk_plan* p, const void* mesh_slab, int mesh_dtype, void* 
                       void* convert_work, void* planes_local) {
   BSK_REQUIRE(p && mesh_slab && work && planes_local, "bsk_forward_local: null argument");
   BSK_REQUIRE(mesh_dtype == BSK_F32 || mesh_dtype == BSK_F64, "bad mesh_dtype %d", mesh_dtype);
+  BSK_REQUIRE(mesh_dtype == BSK_F64 || convert_work,
+              "float32 mesh: convert_work (fwd_batch*N*N float64) is required");
   const bsk_info& f = p->info;
   const int N = p->g.nmesh;
-  const int64_t nreal = f.nxl * (int64_t)N * N;
-  const void* src = mesh_slab;
-  if (mesh_dtype != p->g.precision) {
-    BSK_REQUIRE(convert_work, "mesh dtype differs from plan precision: convert_work required");
-    if (p->g.precision == BSK_F32)
-      convert_kernel<double, float><<<grid_for(nreal, 256), 256, 0, p->stream>>>(
-          (const double*)mesh_slab, (float*)convert_work, nreal);
-    else
-      convert_kernel<float, double><<<grid_for(nreal, 256), 256, 0, p->stream>>>(
-          (const float*)mesh_slab, (double*)convert_work, nreal);
+  const int64_t chunk_real = f.fwd_batch * (int64_t)N * N;
+  const int64_t chunk_out = f.fwd_batch * f.ky * f.kz;
+  const double scale = 1.0 / ((double)N * (double)N * (double)N);
+  for (int64_t c = 0; c < f.nxl / f.fwd_batch; ++c) {
+    const double* src;
+    if (mesh_dtype == BSK_F32) {
+      convert_kernel<float, double><<<grid_for(chunk_real, 256), 256, 0, p->stream>>>(
+          (const float*)mesh_slab + c * chunk_real, (double*)convert_work, chunk_real);
+      count_launch();
+      BSK_CUDA(cudaGetLastError());
+      src = (const double*)convert_work;
+    } else {
+      src = (const double*)mesh_slab + c * chunk_real;
+    }
+    BSK_FFT(cufftExecD2Z(p->fwd2d, (cufftDoubleReal*)src, (cufftDoubleComplex*)work));
+    crop_yz_kernel<double><<<grid_for(chunk_out, 256), 256, 0, p->stream>>>(
+        (const double2*)work, (double2*)planes_local + c * chunk_out, (int)f.fwd_batch, N,
+        (int)f.ky, (int)f.kz, scale, p->d_cy, p->d_cz);
     count_launch();
     BSK_CUDA(cudaGetLastError());
-    src = convert_work;
   }
-  const double scale = 1.0 / ((double)N * (double)N * (double)N);
-  const int64_t total = f.planes_local_complex;
-  if (p->g.precision == BSK_F32) {
-    BSK_FFT(cufftExecR2C(p->fwd2d, (cufftReal*)src, (cufftComplex*)work));
-    crop_yz_kernel<float><<<grid_for(total, 256), 256, 0, p->stream>>>(
-        (const float2*)work, (float2*)planes_local, (int)f.nxl, N, (int)f.ky, (int)f.kz, scale,
-        p->d_cy, p->d_cz);
-  } else {
-    BSK_FFT(cufftExecD2Z(p->fwd2d, (cufftDoubleReal*)src, (cufftDoubleComplex*)work));
-    crop_yz_kernel<double><<<grid_for(total, 256), 256, 0, p->stream>>>(
-        (const double2*)work, (double2*)planes_local, (int)f.nxl, N, (int)f.ky, (int)f.kz, scale,
-        p->d_cy, p->d_cz);
-  }
-  count_launch();
-  BSK_CUDA(cudaGetLastError());
   return BSK_OK;
 }
 
@@ -468,16 +497,10 @@ int bsk_forward_finish(bsk_plan* p, void* planes_all, void* cube) {
   const bsk_info& f = p->info;
   const int N = p->g.nmesh;
   const int64_t plane = f.ky * f.kz;
-  if (p->g.precision == BSK_F32) {
-    BSK_FFT(cufftExecC2C(p->fwdx, (cufftComplex*)planes_all, (cufftComplex*)planes_all, CUFFT_FORWARD));
-    crop_x_kernel<float><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-        (const float2*)planes_all, (float2*)cube, N, (int)f.kx, plane, p->d_cx);
-  } else {
-    BSK_FFT(cufftExecZ2Z(p->fwdx, (cufftDoubleComplex*)planes_all, (cufftDoubleComplex*)planes_all,
-                         CUFFT_FORWARD));
-    crop_x_kernel<double><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-        (const double2*)planes_all, (double2*)cube, N, (int)f.kx, plane, p->d_cx);
-  }
+  BSK_FFT(cufftExecZ2Z(p->fwdx, (cufftDoubleComplex*)planes_all, (cufftDoubleComplex*)planes_all,
+                       CUFFT_FORWARD));
+  crop_x_kernel<double><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
+      (const double2*)planes_all, (double2*)cube, N, (int)f.kx, plane, p->d_cx);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   return BSK_OK;
@@ -525,9 +548,11 @@ int bsk_shells(bsk_plan* p, const void* cube, int kind, double kpow, int nsh, co
     be.hi[s] = hi[s];
   }
   for (int s = nsh; s < kMaxChunk; ++s) be.lo[s] = be.hi[s] = 0.0;
-  return p->g.precision == BSK_F32
-             ? shells_impl<float>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields)
-             : shells_impl<double>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields);
+  if (p->g.precision == BSK_F64)
+    return shells_impl<double, double>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields);
+  return p->g.fft_precision == BSK_F64
+             ? shells_impl<double, float>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields)
+             : shells_impl<float, float>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields);
 }
 
 }  // extern "C"

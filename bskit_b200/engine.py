@@ -152,16 +152,20 @@ class NativeBackend:
 
     name = "cuda-sm100a"
 
-    def __init__(self, grid: GridChoice, boxsize, precision, world, rank, device, max_shells):
+    def __init__(self, grid: GridChoice, boxsize, precision, world, rank, device, max_shells,
+                 fft_precision=None, accum_precision=None):
         if device.type != "cuda":
             raise nat.NativeError("bskit_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = nat.lib()
         self.grid, self.precision, self.device = grid, precision, device
+        self.fft_precision = nat.F64 if fft_precision is None else max(fft_precision, precision)
+        self.accum_precision = precision if accum_precision is None else max(accum_precision, precision)
         self.rdtype = torch.float32 if precision == nat.F32 else torch.float64
-        self.cdtype = torch.complex64 if precision == nat.F32 else torch.complex128
+        self.cdtype = torch.complex64 if self.fft_precision == nat.F32 else torch.complex128
         kx, ky, kz, _ = axis_tables(grid, boxsize)
         self._tables = (kx, ky, kz)
-        geom = nat.Geometry(grid.nmesh, grid.neval, grid.ncrop, precision, world, rank, max_shells, 0)
+        geom = nat.Geometry(grid.nmesh, grid.neval, grid.ncrop, precision, world, rank, max_shells,
+                            self.fft_precision)
         self.stream = torch.cuda.current_stream(device).cuda_stream
         handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -193,14 +197,14 @@ class NativeBackend:
                   "bsk_set_compensation")
 
     def forward_local(self, slab):
-        """slab: CUDA tensor [nxl][N][N] f32/f64 -> planes_local [nxl][Ky][Kz] complex."""
+        """slab: CUDA tensor [nxl][N][N] f32/f64 -> planes_local [nxl][Ky][Kz] complex128."""
         f, n = self.info, self.grid.nmesh
-        work = torch.empty(f.fwd_work_complex, dtype=self.cdtype, device=self.device)
+        work = torch.empty(f.fwd_work_complex, dtype=torch.complex128, device=self.device)
         conv = None
         mesh_dtype = nat.F32 if slab.dtype == torch.float32 else nat.F64
-        if mesh_dtype != self.precision:
-            conv = torch.empty(f.nxl * n * n, dtype=self.rdtype, device=self.device)
-        planes = torch.empty((f.nxl, f.ky, f.kz), dtype=self.cdtype, device=self.device)
+        if mesh_dtype == nat.F32:
+            conv = torch.empty(f.fwd_batch * n * n, dtype=torch.float64, device=self.device)
+        planes = torch.empty((f.nxl, f.ky, f.kz), dtype=torch.complex128, device=self.device)
         nat.check(self.lib.bsk_forward_local(self.handle, slab.data_ptr(), mesh_dtype, work.data_ptr(),
                                              conv.data_ptr() if conv is not None else None,
                                              planes.data_ptr()), "bsk_forward_local")
@@ -208,7 +212,7 @@ class NativeBackend:
 
     def forward_finish(self, planes_all):
         f = self.info
-        cube = torch.empty((f.kx, f.ky, f.kz), dtype=self.cdtype, device=self.device)
+        cube = torch.empty((f.kx, f.ky, f.kz), dtype=torch.complex128, device=self.device)
         nat.check(self.lib.bsk_forward_finish(self.handle, planes_all.data_ptr(), cube.data_ptr()),
                   "bsk_forward_finish")
         return cube
@@ -248,23 +252,25 @@ class NativeBackend:
             ent = (cp, max(njobs, 4))
             self._cplans[key] = ent
         cp = ent[0]
+        self._last_cplan = cp
         sums = torch.empty((njobs, len(rows)), dtype=torch.float64, device=self.device)
         ptrs = (C.c_void_p * nrows)(*row_ptrs)
         with torch.cuda.device(self.device):
-            nat.check(self.lib.bsk_contract(cp, ptrs, self.precision, ncells, njobs,
+            nat.check(self.lib.bsk_contract(cp, ptrs, self.precision, self.accum_precision, ncells, njobs,
                                             job_off.ctypes.data_as(C.POINTER(C.c_int32)),
                                             C.cast(sums.data_ptr(), C.POINTER(C.c_double)),
                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                       "bsk_contract")
         return sums
 
-    def cplan_info(self, rows, nrows):
-        ent = self._cplans.get((np.ascontiguousarray(rows, dtype=np.int32).tobytes(), nrows))
-        if ent is None:
+    def cplan_info(self):
+        """Schedule of the most recent contraction: blocks, split, rounds, threads."""
+        cp = getattr(self, "_last_cplan", None)
+        if cp is None:
             return None
         out = (C.c_int64 * 4)()
-        nat.check(self.lib.bsk_cplan_info(ent[0], out), "bsk_cplan_info")
-        return dict(nblocks=out[0], split=out[1], rounds=out[2], threads=out[3])
+        nat.check(self.lib.bsk_cplan_info(cp, out), "bsk_cplan_info")
+        return dict(nblocks=int(out[0]), split=int(out[1]), rounds=int(out[2]), threads=int(out[3]))
 
 
 # --------------------------------------------------------------------------- #
@@ -274,7 +280,8 @@ class Engine:
     """Shell synthesis + triangle contraction on one (N, M, crop, precision) geometry."""
 
     def __init__(self, grid: GridChoice, boxsize, precision=nat.F32, device=None, group=None,
-                 backend_cls=NativeBackend, scratch_bytes=None):
+                 backend_cls=NativeBackend, scratch_bytes=None, fft_precision=None,
+                 accum_precision=None):
         self.grid = grid
         self.boxsize = box3(boxsize)
         self.precision = precision
@@ -285,22 +292,25 @@ class Engine:
                 else torch.device("cpu")
         self.device = torch.device(device)
         self.itemsize = 4 if precision == nat.F32 else 8
+        fft_precision = nat.F64 if fft_precision is None else max(fft_precision, precision)
+        fft_itemsize = 4 if fft_precision == nat.F32 else 8
         m = grid.neval
         mxl = m // self.world
         kxy = grid.nmesh if grid.full else 2 * grid.ncrop + 1
         kzn = grid.nmesh // 2 + 1 if grid.full else grid.ncrop + 1
-        per_shell = (m * kxy * kzn + mxl * m * (m // 2 + 1)) * 2 * self.itemsize
+        per_shell = (m * kxy * kzn + mxl * m * (m // 2 + 1)) * 2 * fft_itemsize
         if scratch_bytes is None:
             scratch_bytes = 6 << 30
         # keep each cuFFT batch below 2^31 elements and the scratch within budget
         by_elems = (2 ** 31 - 1) // max(mxl * m * m, 1)
         self.chunk = int(max(1, min(nat.MAX_CHUNK, scratch_bytes // max(per_shell, 1), by_elems)))
         self.backend = backend_cls(grid, self.boxsize, precision, self.world, self.rank,
-                                   self.device, self.chunk)
+                                   self.device, self.chunk, fft_precision=fft_precision,
+                                   accum_precision=accum_precision)
         self.info = self.backend.info
         self.ncells = int(self.info.field_real_per_shell)
         self.rdtype = torch.float32 if precision == nat.F32 else torch.float64
-        self.cdtype = torch.complex64 if precision == nat.F32 else torch.complex128
+        self.cdtype = torch.complex64 if fft_precision == nat.F32 else torch.complex128
         self._scratch = None
 
     # -- forward ------------------------------------------------------------ #
@@ -323,7 +333,8 @@ class Engine:
                              f"slab {(f.nxl, n, n)}")
         if t.device != self.device:
             if t.device.type == "cpu" and self.device.type == "cuda":
-                t = t.contiguous().pin_memory().to(self.device, non_blocking=True)
+                t = t.contiguous()
+                t = (t if t.is_pinned() else t.pin_memory()).to(self.device, non_blocking=True)
             else:
                 t = t.to(self.device)
         return t.contiguous()
@@ -365,7 +376,7 @@ class Engine:
             self.backend.shells(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols, planes2d, out[s0:s1])
 
     # -- contraction ---------------------------------------------------------- #
-    def contract(self, table, rows, job_off=((0, 0, 0),)):
+    def contract(self, table, rows, job_off=((0, 0, 0),), marks=None):
         """Triangle sums over this rank's cells, all-reduced over ranks.
 
         table: [nrows][ncells] CUDA tensor of fields (nrows % 4 == 0);
@@ -375,6 +386,7 @@ class Engine:
         base, stride = table.data_ptr(), table.stride(0) * table.element_size()
         ptrs = [base + r * stride for r in range(nrows)]
         sums = self.backend.contract(rows, nrows, ptrs, self.ncells, job_off)
+        _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         return sums.cpu().numpy()
@@ -413,7 +425,15 @@ def _unique_triples(triples):
     return uniq, np.asarray(inverse).reshape(-1)
 
 
-def measure_triangle_sums(engine: Engine, cubes, edges, triples):
+def _mark(marks, name, engine):
+    """Optional stage timing hook: record a CUDA event on the launching stream."""
+    if marks is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(engine.device))
+        marks.append((name, ev))
+
+
+def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None):
     """sum_x I_a I_b I_c / M^3 for every (a,b,c) in `triples` (indices into `edges`).
 
     cubes: 1-3 spectrum cubes (auto, <AAB>, <ABC> routing as the reference's slow
@@ -437,12 +457,13 @@ def measure_triangle_sums(engine: Engine, cubes, edges, triples):
             filled[arr * sp + np.asarray(run)] = True
     _fill_unused(table, filled)
     rows = np.stack([uniq[:, s] + route[s] * sp for s in range(3)], axis=1)
-    sums = engine.contract(table, rows)[0]
+    _mark(marks, "shells_done", engine)
+    sums = engine.contract(table, rows, marks=marks)[0]
     del table
     return sums[inverse] / float(engine.grid.neval) ** 3
 
 
-def measure_grid_sums(engine: Engine, edges, triples):
+def measure_grid_sums(engine: Engine, edges, triples, marks=None):
     """(N_tri, k_mean[T,3]) from unit-amplitude and |k|-weighted shells
     (main.py:2006-2061): N_tri = sum n_a n_b n_c / M^3, k_1 = sum kappa_a n_b n_c / M^3 / N_tri ..."""
     edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
@@ -460,7 +481,8 @@ def measure_grid_sums(engine: Engine, edges, triples):
         filled[sp + np.asarray(run)] = True
     _fill_unused(table, filled)
     jobs = ((0, 0, 0), (sp, 0, 0), (0, sp, 0), (0, 0, sp))
-    sums = engine.contract(table, uniq, jobs) / float(engine.grid.neval) ** 3
+    _mark(marks, "shells_done", engine)
+    sums = engine.contract(table, uniq, jobs, marks=marks) / float(engine.grid.neval) ** 3
     del table
     ntri = np.rint(sums[0])                      # an exact triangle count (integer valued)
     with np.errstate(divide="ignore", invalid="ignore"):

@@ -58,8 +58,11 @@ F32, F64 = 0, 1
 class _Session:
     """Engines for one (Nmesh, BoxSize) pair on this process's GPU."""
 
-    def __init__(self, nmesh, boxsize, grid="auto", device=None, group=None):
+    def __init__(self, nmesh, boxsize, grid="auto", device=None, group=None, fft_dtype=None,
+                 accum_dtype=None):
         from . import engine as eng
+        self.fft_precision = None if fft_dtype is None else (F32 if np.dtype(fft_dtype) == np.float32 else F64)
+        self.accum_precision = None if accum_dtype is None else (F32 if np.dtype(accum_dtype) == np.float32 else F64)
         self.eng = eng
         self.nmesh = int(nmesh)
         self.boxsize = eng.box3(boxsize)
@@ -75,7 +78,9 @@ class _Session:
         key = (choice, precision)
         if key not in self._engines:
             self._engines[key] = self.eng.Engine(choice, self.boxsize, precision,
-                                                 device=self.device, group=self.group)
+                                                 device=self.device, group=self.group,
+                                                 fft_precision=self.fft_precision,
+                                                 accum_precision=self.accum_precision)
         return self._engines[key]
 
     def compensation_tables(self, engine, comp):
@@ -135,12 +140,13 @@ def _bins_table(bins3_list):
 class _Measurer:
     """Shared implementation behind the class methods and the module functions."""
 
-    def __init__(self, meshes, grid="auto", compute_dtype=None, device=None, group=None):
+    def __init__(self, meshes, grid="auto", compute_dtype=None, device=None, group=None,
+                 fft_dtype=None, accum_dtype=None):
         first = meshes[0]
         self.meshes = meshes
         self.nmesh = int(first.attrs["Nmesh"][0])
         self.boxsize = np.asarray(first.attrs["BoxSize"], dtype=np.float64)
-        self.session = _Session(self.nmesh, self.boxsize, grid, device, group)
+        self.session = _Session(self.nmesh, self.boxsize, grid, device, group, fft_dtype, accum_dtype)
         if compute_dtype is None:
             # the reference computes in the mesh's own dtype (f4 meshes -> f4 fields)
             self.precision = F32 if all(_mesh_dtype_code(m) == F32 for m in meshes) else F64
@@ -171,7 +177,9 @@ class _Measurer:
     def gridinfo(self, edges, triples):
         """(N_tri, k_mean) — always float64 like the reference's f8 number/k fields."""
         edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
-        e = self.session.engine(edges[:, 1].max(), F64)
+        # N_tri and k_mean depend on (BoxSize, bins) only, not on Nmesh while 3 n_max < N
+        # (SURVEY.md B.1), so the exact band-limited grid is always used here
+        e = self.session.engine(edges[:, 1].max(), F64, policy="auto" if self.session.grid_policy == "full" else None)
         return self.session.eng.measure_grid_sums(e, edges, triples)
 
 
@@ -334,9 +342,11 @@ class FFTBispectrum:
 
     Constructor arguments as the reference class (main.py:1414-1459).  Extra
     keyword-only arguments: ``grid`` ('auto' | 'full' | int, see
-    ``engine.choose_grid``), ``compute_dtype`` (default: the mesh dtype, as the
-    reference computes), ``device`` and ``group`` (torch.distributed process group;
-    every rank must make the same calls).
+    ``engine.choose_grid``), ``compute_dtype`` (storage dtype of the shell fields;
+    default: the mesh dtype, as the reference computes), ``fft_dtype`` (precision of
+    the inverse transforms, default float64), ``accum_dtype`` (precision of the triple
+    products and per-tile sums, default = compute_dtype), ``device`` and ``group``
+    (torch.distributed process group; every rank must make the same calls).
     """
 
     logger = logging.getLogger("FFTBispectrum")
@@ -345,8 +355,8 @@ class FFTBispectrum:
                  num_lowk_bins=0, dk_high=-1.0, dmu=None, mu_min=None, mu_max=None,
                  pos_units_mpcoverh=1.0, k_edges=None, second=None, third=None,
                  triangle_type="all", isos_mult=0, isos_tol=0.1, squeezed_bin_index=0,
-                 for_grid_info_only=False, *, grid="auto", compute_dtype=None, device=None,
-                 group=None):
+                 for_grid_info_only=False, *, grid="auto", compute_dtype=None, fft_dtype=None,
+                 accum_dtype=None, device=None, group=None):
         self.first = cast_source(source, Nmesh=Nmesh, BoxSize=BoxSize)
         self.mesh = self.first
         self.second = None
@@ -400,7 +410,8 @@ class FFTBispectrum:
             self.k_indices = gen(True)
 
         self.b = None
-        self._engine_opts = dict(grid=grid, compute_dtype=compute_dtype, device=device, group=group)
+        self._engine_opts = dict(grid=grid, compute_dtype=compute_dtype, device=device, group=group,
+                                 fft_dtype=fft_dtype, accum_dtype=accum_dtype)
         self._measurer = None
         if not for_grid_info_only:
             self._paint_meshes()

@@ -55,20 +55,27 @@ typedef struct bsk_geometry {
                         reproduces the reference's transforms exactly; M < N is
                         the band-limited evaluation (exact when M > 3*ncrop) */
   int32_t ncrop;     /* keep modes with |n_axis| <= ncrop; >= N/2 keeps all */
-  int32_t precision; /* BSK_F32 or BSK_F64: dtype of spectra and shell fields */
+  int32_t precision; /* BSK_F32 or BSK_F64: storage dtype of the shell fields */
   int32_t world;     /* number of x-slab shards (ranks) */
   int32_t rank;      /* this shard */
   int32_t max_shells;/* largest nsh a bsk_shells() call will pass */
-  int32_t reserved;
+  int32_t fft_precision; /* precision of the inverse transforms (>= precision).  F64
+                        with F32 storage keeps the only float32 rounding per-cell and
+                        uncorrelated; a float32 FFT's correlated error does not average
+                        out of the heavily cancelling triangle sums */
 } bsk_geometry;
 
-/* Derived sizes, bsk_plan_info(): all counts in ELEMENTS of the plan precision
- * (complex counts are numbers of complex values). */
+/* Derived sizes, bsk_plan_info(): counts in ELEMENTS (complex counts are numbers of
+ * complex values).  The forward transform and the spectrum cube are ALWAYS float64 /
+ * complex128 (a float32 FFT's rounding error scales with the rms of the whole spectrum
+ * and would swamp the weak high-k modes); xcols / planes2d are in fft_precision, fields
+ * in precision. */
 typedef struct bsk_info {
   int64_t kx, ky, kz;          /* cropped spectrum cube dims */
   int64_t nx0, nxl;            /* local x-planes of the N grid  [nx0, nx0+nxl) */
   int64_t mx0, mxl;            /* local x-planes of the M grid */
-  int64_t fwd_work_complex;    /* nxl * N * (N/2+1) */
+  int64_t fwd_batch;           /* planes per forward 2-D transform chunk (divides nxl) */
+  int64_t fwd_work_complex;    /* fwd_batch * N * (N/2+1)  (complex128) */
   int64_t planes_local_complex;/* nxl * ky * kz */
   int64_t planes_all_complex;  /* N * ky * kz */
   int64_t cube_complex;        /* kx * ky * kz */
@@ -96,17 +103,17 @@ int bsk_set_compensation(bsk_plan* plan, const double* comp_x, const double* com
                          const double* comp_z);
 
 /* Forward transform of this rank's x-slab (replaces mesh.paint(mode='complex'),
- * main.py:1608-1621, plus the queued compensation action).
- *   mesh_slab    device, [nxl][N][N] real, dtype mesh_dtype (BSK_F32/BSK_F64);
- *                converted to the plan precision if it differs
- *   work         device, fwd_work_complex complex values (+ nxl*N*N reals when a
- *                dtype conversion is needed: pass work2)
- *   planes_local device out, [nxl][ky][kz] complex: 2-D r2c over (y,z), scaled by
+ * main.py:1608-1621, plus the queued compensation action).  Runs in float64, in chunks
+ * of fwd_batch planes.
+ *   mesh_slab    device, [nxl][N][N] real, dtype mesh_dtype (BSK_F32/BSK_F64)
+ *   work         device scratch, fwd_work_complex complex128 values
+ *   convert_work device scratch, fwd_batch*N*N float64 (float32 meshes only, else NULL)
+ *   planes_local device out, [nxl][ky][kz] complex128: 2-D r2c over (y,z), scaled by
  *                1/N^3, y/z compensation applied, cropped to the kept modes */
 int bsk_forward_local(bsk_plan* plan, const void* mesh_slab, int mesh_dtype, void* work,
                       void* convert_work, void* planes_local);
-/* After the host all-gathered planes_local into planes_all [N][ky][kz]:
- * in-place x transform and crop -> cube [kx][ky][kz] (x compensation applied). */
+/* After the host all-gathered planes_local into planes_all [N][ky][kz] (complex128):
+ * in-place x transform and crop -> cube [kx][ky][kz] complex128 (x compensation applied). */
 int bsk_forward_finish(bsk_plan* plan, void* planes_all, void* cube);
 
 /* Exact integer number of full-cube modes in each k-bin (inclusive both ends,
@@ -119,7 +126,7 @@ int bsk_modes_per_bin(bsk_plan* plan, int nbins, const double* lo, const double*
  * main.py:1846-1861 / number_field / k_field): k-shell filter of the cube,
  * inverse x transform, scatter into zero-padded (y,z) half-spectra of the local
  * planes, batched 2-D c2r.
- *   cube     device [kx][ky][kz] complex (ignored for UNIT / KPOW kinds)
+ *   cube     device [kx][ky][kz] complex128 (ignored for UNIT / KPOW kinds)
  *   lo, hi   HOST float64[nsh] bin edges, both inclusive
  *   xcols    device scratch, nsh * xcols_complex_per_shell complex
  *   planes2d device scratch, nsh * planes2d_complex_per_shell complex
@@ -140,9 +147,14 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, roun
  * applies V^2/N^3 etc. and all-reduces across ranks).
  *   row_ptrs  HOST array of nrows DEVICE pointers, one real field of ncells each
  *   job_off   HOST int32[njobs][3] row offsets per job (0,0,0 for plain B)
- *   sums      device out float64 [njobs][ntri]; fp64 accumulation throughout */
-int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int64_t ncells,
-                 int njobs, const int32_t* job_off, double* sums, void* cuda_stream);
+ *   precision        storage dtype of the fields (BSK_F32 / BSK_F64)
+ *   accum_precision  dtype of the products and of the per-tile partial sums: equal to
+ *                    precision, or BSK_F64 for float32 fields (every product and add in
+ *                    float64; ~2x the time).  Tile partials are always folded in float64.
+ *   sums      device out float64 [njobs][ntri] */
+int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int accum_precision,
+                 int64_t ncells, int njobs, const int32_t* job_off, double* sums,
+                 void* cuda_stream);
 
 /* number of kernels this library has launched since load (bench bookkeeping) */
 int64_t bsk_launch_count(void);

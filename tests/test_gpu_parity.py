@@ -31,16 +31,18 @@ def syn():
     return synthetic
 
 
-def assert_b_close(got, want, rtol=RTOL_B):
-    """Per-triangle relative error where B is not accidentally ~0, and an absolute
-    bound tied to the largest |B| everywhere (the sums cancel to ~0 for some bins)."""
+def assert_b_close(got, want, rtol=RTOL_B, atol_rms=1e-6):
+    """|dB_t| <= rtol*|B_t| + atol_rms*rms(B).  The absolute term is needed because a
+    triangle sum is a cancellation residual (for a Gaussian mesh every B is): float32
+    storage of the shell fields puts an error floor of ~1e-7 x rms(B) under each
+    triangle (measured: scripts/dev_precision.py), as the reference's own f4 path does."""
     got, want = np.asarray(got), np.asarray(want)
-    scale = np.abs(want).max()
-    big = np.abs(want) > 1e-3 * scale
-    rel = np.abs(got[big] - want[big]) / np.abs(want[big])
-    assert rel.max() < rtol, f"max relative error {rel.max():.3e}"
-    assert np.abs(got - want).max() < rtol * 1e-1 * scale + 0.0, \
-        f"max abs error / max|B| = {np.abs(got - want).max() / scale:.3e}"
+    rms = np.sqrt(np.mean(want ** 2))
+    excess = np.abs(got - want) - (rtol * np.abs(want) + atol_rms * rms)
+    worst = int(np.argmax(excess))
+    assert excess[worst] <= 0, (f"triangle {worst}: got {got[worst]:.9e} want {want[worst]:.9e} "
+                                f"rel {abs(got[worst]-want[worst])/abs(want[worst]):.2e} "
+                                f"abs/rms {abs(got[worst]-want[worst])/rms:.2e}")
 
 
 # --- C1: 64^3 Gaussian mesh, equilateral bins, auto-bispectrum ---------------------- #
@@ -75,7 +77,10 @@ def test_all_triangles_64(bk, syn, grid, dtype):
     assert np.array_equal(fb.k_edges, e6) and np.array_equal(fb.k_indices, idx)
     got = fb.measure_bispectrum_faster(0, len(idx))
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
-    assert_b_close(got["B"], want, RTOL_B if dtype == np.float32 else 1e-10)
+    if dtype == np.float32:
+        assert_b_close(got["B"], want)
+    else:
+        assert_b_close(got["B"], want, 1e-10, 1e-12)
     gi = fb.measure_gridinfo_faster(0, len(idx))
     wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx, workers=4)
     assert np.array_equal(gi["N_tri"], np.rint(wn))
@@ -97,7 +102,7 @@ def test_aliased_regime_matches_oracle(bk, syn):
     gi = fb.measure_gridinfo_faster(0, len(idx))
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx)
     wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx)
-    assert_b_close(got["B"], want, 1e-10)
+    assert_b_close(got["B"], want, 1e-10, 1e-12)
     assert np.array_equal(gi["N_tri"], np.rint(wn))
     fb.close()
 
@@ -116,7 +121,7 @@ def test_full_spectrum_regime(bk, syn):
     gi = fb.measure_gridinfo_faster(0, len(idx))
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx)
     wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx)
-    assert_b_close(got["B"], want, 1e-10)
+    assert_b_close(got["B"], want, 1e-10, 1e-12)
     assert np.array_equal(gi["N_tri"], np.rint(wn))
     ok = wn > 0.5
     np.testing.assert_allclose(gi["k_mean"][ok], wk[ok], rtol=1e-10)
@@ -210,7 +215,7 @@ def test_cic_compensation(bk, syn):
     got = fb.measure_bispectrum_faster(0, nb)
     want = orc.measure_unnormalized([a], syn.BOX, edges, idx, nmesh_cic=n)
     plain = orc.measure_unnormalized([a], syn.BOX, edges, idx)
-    assert_b_close(got["B"], want, 1e-10)
+    assert_b_close(got["B"], want, 1e-10, 1e-12)
     assert np.abs(want - plain).max() > 1e-3 * np.abs(want).max()     # the compensation matters
     fb.close()
 
@@ -281,5 +286,21 @@ def test_band_limited_grid_equals_full_grid_256(bk, syn):
     _, idx = orc.triangles_all(edges, 1)
     pick = np.linspace(0, len(idx) - 1, 6).astype(int)
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx[pick], workers=8)
-    rel = np.abs(res["full"][pick] - want) / np.abs(want)
-    assert rel.max() < RTOL_B, rel
+    assert_b_close(res["full"][pick], want)
+
+
+def test_float64_accumulation_mode_is_tighter(bk, syn):
+    """accum_dtype=float64 (every product and add in float64 on float32 fields): 1e-5
+    relative holds down to |B| = 1e-3 max|B| even on a Gaussian mesh."""
+    n, nb = 64, 12
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.gaussian_mesh(n, seed=1)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="full",
+                          accum_dtype=np.float64)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    got = fb.measure_bispectrum_faster(0, len(idx))["B"]
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
+    big = np.abs(want) > 1e-3 * np.abs(want).max()
+    assert (np.abs(got - want)[big] / np.abs(want)[big]).max() < RTOL_B
+    fb.close()
