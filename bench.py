@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--nbins", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--accum", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--profile", action="store_true",
+                    help="only the full-grid device-resident steps (for ncu); prints stage times")
     return ap.parse_args()
 
 
@@ -293,7 +295,12 @@ def main():
         torch.cuda.empty_cache()
         return res
 
-    full = timed("full", args.steps, args.warmup, with_clocks=True)
+    full = timed("full", args.steps, args.warmup, with_clocks=not args.profile)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": full["ms_per_step"],
+                              "stages_ms": full["stages_ms"], "gpu_launches": full["launches"]}))
+        return
     auto = timed("auto", args.steps, args.warmup)
 
     # ---- e2e: the user-facing API from (pinned) host memory, result back on the host

@@ -234,8 +234,12 @@ class NativeBackend:
                                       xcols.data_ptr(), planes2d.data_ptr(), fields_out.data_ptr()),
                   "bsk_shells")
 
-    def contract(self, rows, nrows, row_ptrs, ncells, job_off):
-        """rows: (T,3) int32 tile-row triples; returns local float64 sums [njobs][T] (CUDA)."""
+    def contract(self, table, rows, ncells, job_off):
+        """table: [nrows][ncells] fields; rows: (T,3) int32 row triples into it.
+        Returns this rank's float64 sums [njobs][T] (CUDA tensor)."""
+        nrows = table.shape[0]
+        base, stride = table.data_ptr(), table.stride(0) * table.element_size()
+        row_ptrs = [base + r * stride for r in range(nrows)]
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         job_off = np.ascontiguousarray(job_off, dtype=np.int32).reshape(-1, 3)
         njobs = len(job_off)
@@ -382,10 +386,7 @@ class Engine:
         table: [nrows][ncells] CUDA tensor of fields (nrows % 4 == 0);
         rows: (T,3) row triples into `table`.  Returns float64 numpy [njobs][T].
         """
-        nrows = table.shape[0]
-        base, stride = table.data_ptr(), table.stride(0) * table.element_size()
-        ptrs = [base + r * stride for r in range(nrows)]
-        sums = self.backend.contract(rows, nrows, ptrs, self.ncells, job_off)
+        sums = self.backend.contract(table, rows, self.ncells, job_off)
         _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
@@ -427,7 +428,7 @@ def _unique_triples(triples):
 
 def _mark(marks, name, engine):
     """Optional stage timing hook: record a CUDA event on the launching stream."""
-    if marks is not None:
+    if marks is not None and engine.device.type == "cuda":
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream(engine.device))
         marks.append((name, ev))
