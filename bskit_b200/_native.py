@@ -27,7 +27,7 @@ EXPORTS = (
 
 class Geometry(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "fft_precision")]
+                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "fft_precision", "no_prune", "reserved")]
 
 
 class Info(C.Structure):

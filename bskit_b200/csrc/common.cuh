@@ -53,6 +53,10 @@ __host__ __device__ inline int mode_of(int j, int k, int n) {
   return j <= nc ? j : j - k;
 }
 
+bool zpass_supported(int M);
+int zpass_run(int M, bool store_f32, const void* xcols, void* ycols, void* fields, int Ky, int Kz,
+              int nsh, int mx0, int mxl, const double2* wtab, cufftHandle yplan, cudaStream_t st);
+
 }  // namespace bsk
 
 struct bsk_plan {
@@ -72,5 +76,8 @@ struct bsk_plan {
   cufftHandle fwdx = 0;    // strided 1-D C2C/Z2Z along x, length N
   std::map<int, cufftHandle> invx;   // by nsh: strided 1-D inverse along x, length M
   std::map<int, cufftHandle> inv2d;  // by nsh: batched 2-D C2R/Z2D
+  std::map<int, cufftHandle> invy;   // by nsh: pruned path, 1-D inverse along y on kept kz columns
+  bool use_zpass = false;            // pruned y/z passes (float64 transforms, power-of-two M)
+  double2* d_wtab = nullptr;         // e^{2 pi i j/M}, j < M
   size_t fft_work_bytes = 0;
 };

@@ -270,6 +270,24 @@ static int get_inv2d(bsk_plan* p, int nsh, cufftHandle* out) {
   return BSK_OK;
 }
 
+static int get_invy(bsk_plan* p, int nsh, cufftHandle* out) {
+  auto it = p->invy.find(nsh);
+  if (it != p->invy.end()) {
+    *out = it->second;
+    return BSK_OK;
+  }
+  long long M = p->g.neval;
+  long long n[1] = {M};
+  long long emb[1] = {M};
+  cufftHandle h;
+  int rc = make_plan_many(&h, 1, n, emb, 1, M, emb, 1, M, CUFFT_Z2Z,
+                          (long long)nsh * p->info.mxl * p->info.kz, p->stream, &p->fft_work_bytes);
+  if (rc) return rc;
+  p->invy[nsh] = h;
+  *out = h;
+  return BSK_OK;
+}
+
 }  // namespace bsk
 
 using namespace bsk;
@@ -304,11 +322,17 @@ static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int
   cufftHandle hx, h2;
   int rc;
   if ((rc = get_invx(p, nsh, &hx))) return rc;
-  if ((rc = get_inv2d(p, nsh, &h2))) return rc;
   if (sizeof(TF) == 4)
     BSK_FFT(cufftExecC2C(hx, (cufftComplex*)xcols, (cufftComplex*)xcols, CUFFT_INVERSE));
   else
     BSK_FFT(cufftExecZ2Z(hx, (cufftDoubleComplex*)xcols, (cufftDoubleComplex*)xcols, CUFFT_INVERSE));
+  if (p->use_zpass) {  // pruned y pass (cuFFT on the kept kz columns) + fused z pass
+    cufftHandle hy;
+    if ((rc = get_invy(p, nsh, &hy))) return rc;
+    return zpass_run(M, sizeof(TS) == 4, xcols, planes2d, fields, (int)f.ky, (int)f.kz, nsh,
+                     (int)f.mx0, (int)f.mxl, p->d_wtab, hy, p->stream);
+  }
+  if ((rc = get_inv2d(p, nsh, &h2))) return rc;
   const int64_t rows = (int64_t)nsh * f.mxl * M;
   int grid = (int)(rows < 148 * 32 ? rows : 148 * 32);
   scatter_planes_kernel<TF><<<grid, 128, 0, p->stream>>>((const C*)xcols, (C*)planes2d, M, (int)f.ky,
@@ -389,7 +413,9 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   f.planes_all_complex = (int64_t)N * f.ky * f.kz;
   f.cube_complex = f.kx * f.ky * f.kz;
   f.xcols_complex_per_shell = (int64_t)M * f.ky * f.kz;
-  f.planes2d_complex_per_shell = f.mxl * (int64_t)M * (M / 2 + 1);
+  p->use_zpass = (g.fft_precision == BSK_F64) && zpass_supported(M) && !g.no_prune;
+  f.planes2d_complex_per_shell =
+      p->use_zpass ? f.mxl * (int64_t)M * f.kz : f.mxl * (int64_t)M * (M / 2 + 1);
   f.field_real_per_shell = f.mxl * (int64_t)M * M;
 
   int rc;
@@ -418,6 +444,22 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
                         &p->fft_work_bytes);
     if (rc) return rc;
   }
+  if (p->use_zpass) {
+    std::vector<double2> w((size_t)M);
+    for (int j = 0; j < M; ++j) {
+      const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)j / (double)M;
+      w[j] = make_double2(cos(a), sin(a));
+    }
+    // exact values on the axes and diagonals keep the table symmetric
+    for (int j = 0; j < M; ++j) {
+      if (j % (M / 4) == 0) {
+        const int q = j / (M / 4);
+        w[j] = make_double2(q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0, q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0);
+      }
+    }
+    BSK_CUDA(cudaMalloc((void**)&p->d_wtab, sizeof(double2) * (size_t)M));
+    BSK_CUDA(cudaMemcpy(p->d_wtab, w.data(), sizeof(double2) * (size_t)M, cudaMemcpyHostToDevice));
+  }
   f.fft_work_bytes = (int64_t)p->fft_work_bytes;
   *out = p;
   return BSK_OK;
@@ -429,6 +471,8 @@ int bsk_plan_destroy(bsk_plan* p) {
   if (p->fwdx) cufftDestroy(p->fwdx);
   for (auto& kv : p->invx) cufftDestroy(kv.second);
   for (auto& kv : p->inv2d) cufftDestroy(kv.second);
+  for (auto& kv : p->invy) cufftDestroy(kv.second);
+  cudaFree(p->d_wtab);
   cudaFree(p->d_kx);
   cudaFree(p->d_ky);
   cudaFree(p->d_kz);

@@ -1,0 +1,208 @@
+// Pruned shell synthesis for power-of-two evaluation grids (sm_100a).
+//
+// The reference materialises, per k-bin, a full zero-padded half spectrum and runs a full 3-D
+// c2r on it (bskit/main.py:1859-1861).  A shell only has modes with |n_axis| <= n_c, so here
+//   x pass : cuFFT on the Ky*Kz kept columns                      (spectral.cu)
+//   y pass : scatter_y_kernel -> [plane][kz][y] zero-padded in y only, cuFFT Z2Z along y
+//            on the Kz kept columns (a factor (M/2+1)/Kz less data than the 2-D transform)
+//   z pass : zpass_c2r_kernel — reads the Kz kept coefficients of a row, does the length-M
+//            real inverse FFT in shared memory / registers in float64 (zfft_core.h) and writes
+//            the row once, already narrowed to the storage dtype.
+// HBM traffic per shell drops from ~5 full-grid passes to one N^3 write plus O(N^2 Kz) reads.
+#include "common.cuh"
+#include "zfft_core.h"
+
+namespace bsk {
+
+using zfft::cplx;
+
+// [x][nsh][Ky][Kz] (after the x transform) -> [nsh][mxl][Kz][M]  (y contiguous, zero padded)
+__global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __restrict__ ycols,
+                                 int M, int Ky, int Kz, int nsh, int mx0, int mxl) {
+  const int nc = (Ky - 1) / 2;
+  const int64_t total = (int64_t)nsh * mxl * Kz * M;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int iy = (int)(i % M);
+    int64_t r = i / M;
+    const int kz = (int)(r % Kz);
+    r /= Kz;
+    const int xl = (int)(r % mxl);
+    const int s = (int)(r / mxl);
+    int jy;
+    if (Ky == M) jy = iy;
+    else if (iy <= nc) jy = iy;
+    else if (iy >= M - nc) jy = iy - M + Ky;
+    else jy = -1;
+    double2 v = make_double2(0.0, 0.0);
+    if (jy >= 0) v = xcols[(((int64_t)(mx0 + xl) * nsh + s) * Ky + jy) * Kz + kz];
+    ycols[i] = v;
+  }
+}
+
+__device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }  // 1 pad per 16 complex
+
+// One Stockham stage of radix R on the rows of this CTA.  TPR threads cooperate on a row.
+template <int R, int H, int TPR>
+__device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, int p, bool active,
+                                               const double2* __restrict__ wtab /* e^{2 pi i j/(2H)} */) {
+  constexpr int T = H / R;          // butterflies per row in this stage
+  constexpr int PER = T / TPR;      // butterflies per thread (TPR = H/16, so PER = 16/R)
+  cplx v[PER][R];
+  if (active) {
+#pragma unroll
+  for (int b = 0; b < PER; ++b) {
+    const int i = lt + b * TPR;
+    const int k = i & (p - 1);
+    const int step = (H / (p * R)) * k;  // twiddle e^{2 pi i k m/(pR)} = wtab[2*step*m]
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      cplx u = row[padidx(i + m * T)];
+      if (m > 0 && p > 1) {
+        const double2 w = __ldg(&wtab[(2 * step * m) & (2 * H - 1)]);
+        u = zfft::cmul(u, cplx{w.x, w.y});
+      }
+      v[b][m] = u;
+    }
+  }
+  }
+  __syncthreads();  // every input of the stage has been read: the buffer can be overwritten
+  if (active) {
+#pragma unroll
+  for (int b = 0; b < PER; ++b) {
+    zfft::dft_inverse_bitrev<R>(v[b]);
+    const int i = lt + b * TPR;
+    const int k = i & (p - 1);
+    const int j = (i - k) * R + k;
+#pragma unroll
+    for (int m = 0; m < R; ++m) row[padidx(j + m * p)] = v[b][zfft::bitrev<R>(m)];
+  }
+  }
+  __syncthreads();
+}
+
+template <int H, int TPR, int P0, int REM>
+struct Stages {
+  static __device__ __forceinline__ void run(cplx* row, int lt, bool active, const double2* wtab) {
+    constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
+    stockham_stage<R, H, TPR>(row, lt, P0, active, wtab);
+    if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, wtab);
+  }
+};
+
+// M = 2H.  Rows are (plane, y); a CTA handles RPC consecutive y of one plane.
+template <int H, typename TS>
+__global__ void __launch_bounds__(256)
+zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
+                 TS* __restrict__ fields,            // [planes][M][M]
+                 int Kz, int64_t planes, const double2* __restrict__ wtab) {
+  constexpr int M = 2 * H;
+  constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;   // threads per row
+  constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;  // rows per CTA
+  constexpr int NT = RPC * TPR;                      // active threads
+  constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1; // padded complex per row
+  extern __shared__ __align__(16) unsigned char zsm[];
+  cplx* sm = reinterpret_cast<cplx*>(zsm);
+
+  const int tid = threadIdx.x;
+  const int64_t groups_per_plane = M / RPC;
+  const int64_t ngroups = planes * groups_per_plane;
+  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int64_t plane = grp / groups_per_plane;
+    const int y0 = (int)(grp - plane * groups_per_plane) * RPC;
+    // ---- load the kept coefficients: X[kz] for kz < Kz, zero elsewhere (incl. index H)
+    for (int e = tid; e < RPC * (H + 1); e += blockDim.x) {
+      const int r = e % RPC, kz = e / RPC;
+      cplx v{0.0, 0.0};
+      if (kz < Kz) {
+        const double2 g = ycols[((int64_t)plane * Kz + kz) * M + y0 + r];
+        v = cplx{g.x, g.y};
+      }
+      sm[r * ROWLEN + padidx(kz)] = v;
+    }
+    __syncthreads();
+    if (tid < NT) {
+      const int r = tid / TPR, lt = tid % TPR;
+      cplx* row = sm + r * ROWLEN;
+      // ---- pack the Hermitian half spectrum into a complex sequence of length H (in place)
+      for (int k = lt; k <= H / 2; k += TPR) {
+        const cplx xk = row[padidx(k)], xhk = row[padidx(H - k)];
+        const double2 w = __ldg(&wtab[k]);
+        cplx zk, zhk;
+        zfft::pack_pair(xk, xhk, cplx{w.x, w.y}, zk, zhk);
+        row[padidx(k)] = zk;
+        if (k != 0 && k != H - k) row[padidx(H - k)] = zhk;
+      }
+    }
+    __syncthreads();
+    // ---- Stockham stages: every thread runs the barriers, threads without a row do no work
+    {
+      const bool active = tid < NT;
+      const int r = active ? tid / TPR : 0;
+      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, wtab);
+    }
+    // ---- write the rows: x[2n] = Re z[n], x[2n+1] = Im z[n]; z[n] is stored at padidx(n)
+    for (int e = tid; e < RPC * H; e += blockDim.x) {
+      const int r = e / H, n = e % H;
+      const cplx z = sm[r * ROWLEN + padidx(n)];
+      TS* dst = fields + ((int64_t)plane * M + y0 + r) * M + 2 * n;
+      if (sizeof(TS) == 4)
+        *reinterpret_cast<float2*>(dst) = make_float2((float)z.x, (float)z.y);
+      else
+        *reinterpret_cast<double2*>(dst) = make_double2(z.x, z.y);
+    }
+    __syncthreads();
+  }
+}
+
+template <int H, typename TS>
+static int launch_zpass(const void* ycols, void* fields, int Kz, int64_t planes, const double2* wtab,
+                        cudaStream_t st) {
+  constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;
+  constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;
+  constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1;
+  const size_t smem = (size_t)RPC * ROWLEN * sizeof(cplx);
+  BSK_CUDA(cudaFuncSetAttribute(zpass_c2r_kernel<H, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  const int64_t ngroups = planes * (2 * H / RPC);
+  const int grid = (int)(ngroups < 148 * 8 ? ngroups : 148 * 8);
+  zpass_c2r_kernel<H, TS><<<grid, 256, smem, st>>>((const double2*)ycols, (TS*)fields, Kz, planes, wtab);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  return BSK_OK;
+}
+
+bool zpass_supported(int M) {
+  return M == 64 || M == 128 || M == 256 || M == 512 || M == 1024 || M == 2048;
+}
+
+// ycols scratch must hold nsh*mxl*Kz*M complex128; wtab = e^{2 pi i j/M}, j < M
+int zpass_run(int M, bool store_f32, const void* xcols, void* ycols, void* fields, int Ky, int Kz,
+              int nsh, int mx0, int mxl, const double2* wtab, cufftHandle yplan, cudaStream_t st) {
+  const int64_t total = (int64_t)nsh * mxl * Kz * M;
+  int64_t g = (total + 255) / 256;
+  scatter_y_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(
+      (const double2*)xcols, (double2*)ycols, M, Ky, Kz, nsh, mx0, mxl);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  BSK_FFT(cufftExecZ2Z(yplan, (cufftDoubleComplex*)ycols, (cufftDoubleComplex*)ycols, CUFFT_INVERSE));
+  const int64_t planes = (int64_t)nsh * mxl;
+#define BSK_ZP(HH)                                                                          \
+  case 2 * HH:                                                                              \
+    return store_f32 ? launch_zpass<HH, float>(ycols, fields, Kz, planes, wtab, st)         \
+                     : launch_zpass<HH, double>(ycols, fields, Kz, planes, wtab, st);
+  switch (M) {
+    BSK_ZP(32)
+    BSK_ZP(64)
+    BSK_ZP(128)
+    BSK_ZP(256)
+    BSK_ZP(512)
+    BSK_ZP(1024)
+    default:
+      set_error("zpass_run: unsupported M=%d", M);
+      return BSK_ERR_ARG;
+  }
+#undef BSK_ZP
+}
+
+}  // namespace bsk

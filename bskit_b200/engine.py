@@ -153,7 +153,7 @@ class NativeBackend:
     name = "cuda-sm100a"
 
     def __init__(self, grid: GridChoice, boxsize, precision, world, rank, device, max_shells,
-                 fft_precision=None, accum_precision=None):
+                 fft_precision=None, accum_precision=None, no_prune=False):
         if device.type != "cuda":
             raise nat.NativeError("bskit_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = nat.lib()
@@ -165,7 +165,7 @@ class NativeBackend:
         kx, ky, kz, _ = axis_tables(grid, boxsize)
         self._tables = (kx, ky, kz)
         geom = nat.Geometry(grid.nmesh, grid.neval, grid.ncrop, precision, world, rank, max_shells,
-                            self.fft_precision)
+                            self.fft_precision, int(bool(no_prune)), 0)
         self.stream = torch.cuda.current_stream(device).cuda_stream
         handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -285,7 +285,7 @@ class Engine:
 
     def __init__(self, grid: GridChoice, boxsize, precision=nat.F32, device=None, group=None,
                  backend_cls=NativeBackend, scratch_bytes=None, fft_precision=None,
-                 accum_precision=None):
+                 accum_precision=None, no_prune=False):
         self.grid = grid
         self.boxsize = box3(boxsize)
         self.precision = precision
@@ -302,7 +302,8 @@ class Engine:
         mxl = m // self.world
         kxy = grid.nmesh if grid.full else 2 * grid.ncrop + 1
         kzn = grid.nmesh // 2 + 1 if grid.full else grid.ncrop + 1
-        per_shell = (m * kxy * kzn + mxl * m * (m // 2 + 1)) * 2 * fft_itemsize
+        pruned = (fft_precision == nat.F64 and not no_prune and m in (64, 128, 256, 512, 1024, 2048))
+        per_shell = (m * kxy * kzn + mxl * m * (kzn if pruned else m // 2 + 1)) * 2 * fft_itemsize
         if scratch_bytes is None:
             scratch_bytes = 6 << 30
         # keep each cuFFT batch below 2^31 elements and the scratch within budget
@@ -310,7 +311,7 @@ class Engine:
         self.chunk = int(max(1, min(nat.MAX_CHUNK, scratch_bytes // max(per_shell, 1), by_elems)))
         self.backend = backend_cls(grid, self.boxsize, precision, self.world, self.rank,
                                    self.device, self.chunk, fft_precision=fft_precision,
-                                   accum_precision=accum_precision)
+                                   accum_precision=accum_precision, no_prune=no_prune)
         self.info = self.backend.info
         self.ncells = int(self.info.field_real_per_shell)
         self.rdtype = torch.float32 if precision == nat.F32 else torch.float64

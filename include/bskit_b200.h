@@ -63,6 +63,10 @@ typedef struct bsk_geometry {
                         with F32 storage keeps the only float32 rounding per-cell and
                         uncorrelated; a float32 FFT's correlated error does not average
                         out of the heavily cancelling triangle sums */
+  int32_t no_prune;  /* 1 = always use the generic cuFFT 2-D c2r path (debug / A-B timing);
+                        0 = use the pruned y pass + fused z-pass kernel when neval is a
+                        power of two in [64, 2048] and fft_precision is F64 */
+  int32_t reserved;
 } bsk_geometry;
 
 /* Derived sizes, bsk_plan_info(): counts in ELEMENTS (complex counts are numbers of
@@ -80,7 +84,7 @@ typedef struct bsk_info {
   int64_t planes_all_complex;  /* N * ky * kz */
   int64_t cube_complex;        /* kx * ky * kz */
   int64_t xcols_complex_per_shell;  /* M * ky * kz       (W buffer) */
-  int64_t planes2d_complex_per_shell;/* mxl * M * (M/2+1) (P buffer) */
+  int64_t planes2d_complex_per_shell;/* mxl * M * (M/2+1), or mxl * M * kz on the pruned path */
   int64_t field_real_per_shell;     /* mxl * M * M = local cells */
   int64_t fft_work_bytes;      /* cuFFT work areas owned by the plan */
 } bsk_info;

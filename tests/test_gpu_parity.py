@@ -304,3 +304,37 @@ def test_float64_accumulation_mode_is_tighter(bk, syn):
     big = np.abs(want) > 1e-3 * np.abs(want).max()
     assert (np.abs(got - want)[big] / np.abs(want)[big]).max() < RTOL_B
     fb.close()
+
+
+@pytest.mark.parametrize("n,nb,prec", [(64, 12, "f32"), (64, 30, "f64"), (128, 20, "f32"), (128, 62, "f64")])
+def test_pruned_zpass_equals_generic_cufft_path(bk, syn, n, nb, prec):
+    """The fused z-pass kernel (power-of-two grids) against the generic cuFFT 2-D c2r path on
+    the same spectrum cube, cropped (nb small) and full-spectrum (bins up to Nyquist) cases."""
+    import torch
+    from bskit_b200 import engine as eng, _native as nat
+    kmin, kmax, dk = syn.bench_bins(nb)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    mesh = syn.lognormal_mesh(n, seed=7, dtype=np.float64)
+    g = eng.choose_grid(n, syn.BOX, edges[:, 1].max(), "full")
+    P = nat.F32 if prec == "f32" else nat.F64
+    dev = torch.device("cuda", 0)
+    out = {}
+    for no_prune in (False, True):
+        e = eng.Engine(g, syn.BOX, P, device=dev, no_prune=no_prune)
+        cube = e.forward(mesh)
+        t = torch.empty((len(edges), e.ncells), dtype=e.rdtype, device=dev)
+        e.synthesize(cube, nat.KIND_DATA, 0.0, edges[:, 0], edges[:, 1], t)
+        k = torch.empty((len(edges), e.ncells), dtype=e.rdtype, device=dev)
+        e.synthesize(None, nat.KIND_KPOW, 1.0, edges[:, 0], edges[:, 1], k)
+        out[no_prune] = (t.double().cpu().numpy(), k.double().cpu().numpy())
+        e.close()
+    tol = 3e-7 if prec == "f32" else 1e-12
+    for a, b in zip(out[False], out[True]):
+        scale = np.abs(b).max(axis=1, keepdims=True)
+        assert (np.abs(a - b) / scale).max() < tol
+    # and against the oracle's shells
+    dk64 = orc.forward(mesh)
+    kk = orc.k_norm(n, syn.BOX)
+    for i in (0, len(edges) // 2, len(edges) - 1):
+        want = orc.data_shell(dk64, kk, edges[i, 0], edges[i, 1]).reshape(-1)
+        assert np.abs(out[False][0][i] - want).max() / np.abs(want).max() < tol
