@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <unordered_map>
 
 namespace bsk {
@@ -82,8 +83,12 @@ template <> struct Vec<double> {
   }
 };
 
-// T: storage type of the fields; TC: type of the products and per-tile accumulators
-template <typename T, typename TC>
+// T: storage type of the fields; TC: type of the products and per-tile accumulators.
+// PACKED (float/float only): two cells per instruction with Blackwell's packed FP32 math
+// (FMUL2 / FFMA2, fma.rn.f32x2): the (x,y) and (z,w) halves of each 128-bit shared-memory load
+// are already aligned register pairs, so the inner loop issues half as many instructions for the
+// same FMA-pipe work and keeps two partial sums (even / odd cells) per accumulator.
+template <typename T, typename TC, int PACKED>
 __global__ void __launch_bounds__(kThreads, 1)
 tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
                      const int4* __restrict__ blocks, int nblocks, int split, int njobs,
@@ -150,6 +155,92 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
         const V* pa = tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0;
         const V* pb = tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0;
         const V* pc = tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0;
+        double* dst = my_partial + (int64_t)job * 64 * nblocks + b;
+        if constexpr (PACKED == 2) {
+          // 64-bit loads (2 cells), operands of the next step prefetched while this one computes
+          float2 acc2[64];
+#pragma unroll
+          for (int e = 0; e < 64; ++e) acc2[e] = make_float2(0.f, 0.f);
+          const float2* ha = reinterpret_cast<const float2*>(pa);
+          const float2* hb = reinterpret_cast<const float2*>(pb);
+          const float2* hc = reinterpret_cast<const float2*>(pc);
+          const int n2 = 2 * n, rs2 = 2 * rowstride_v;
+          int q = lane % n2;
+          float2 a2[4], b2[4], c2[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            a2[r] = ha[(size_t)r * rs2 + q];
+            b2[r] = hb[(size_t)r * rs2 + q];
+            c2[r] = hc[(size_t)r * rs2 + q];
+          }
+#pragma unroll 1
+          for (int i = 0; i < n2; ++i) {
+            q = q + 1 == n2 ? 0 : q + 1;
+            float2 na[4], nb[4], nc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {      // one step ahead (the last prefetch is unused)
+              na[r] = ha[(size_t)r * rs2 + q];
+              nb[r] = hb[(size_t)r * rs2 + q];
+              nc[r] = hc[(size_t)r * rs2 + q];
+            }
+#pragma unroll
+            for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const float2 pr = __fmul2_rn(a2[i1], b2[i2]);
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3)
+                  acc2[(i1 * 4 + i2) * 4 + i3] = __ffma2_rn(pr, c2[i3], acc2[(i1 * 4 + i2) * 4 + i3]);
+              }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              a2[r] = na[r];
+              b2[r] = nb[r];
+              c2[r] = nc[r];
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            atomicAdd(dst + (int64_t)e * nblocks, (double)acc2[e].x + (double)acc2[e].y);
+        } else if constexpr (PACKED == 1) {
+          float2 acc2[64];
+#pragma unroll
+          for (int e = 0; e < 64; ++e) acc2[e] = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int i = 0; i < n; ++i) {
+            int q = i + rot;
+            if (q >= n) q -= n;
+            float4 va[4], vb[4], vc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              va[r] = pa[(size_t)r * rowstride_v + q];
+              vb[r] = pb[(size_t)r * rowstride_v + q];
+              vc[r] = pc[(size_t)r * rowstride_v + q];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float2 a2[4], b2[4], c2[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                a2[r] = h ? make_float2(va[r].z, va[r].w) : make_float2(va[r].x, va[r].y);
+                b2[r] = h ? make_float2(vb[r].z, vb[r].w) : make_float2(vb[r].x, vb[r].y);
+                c2[r] = h ? make_float2(vc[r].z, vc[r].w) : make_float2(vc[r].x, vc[r].y);
+              }
+#pragma unroll
+              for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2) {
+                  const float2 pr = __fmul2_rn(a2[i1], b2[i2]);
+#pragma unroll
+                  for (int i3 = 0; i3 < 4; ++i3)
+                    acc2[(i1 * 4 + i2) * 4 + i3] = __ffma2_rn(pr, c2[i3], acc2[(i1 * 4 + i2) * 4 + i3]);
+                }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            atomicAdd(dst + (int64_t)e * nblocks, (double)acc2[e].x + (double)acc2[e].y);
+        } else {
         TC acc[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) acc[e] = (TC)0;
@@ -176,9 +267,9 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
                   acc[(i1 * 4 + i2) * 4 + i3] = fma(pr, c[i3][w], acc[(i1 * 4 + i2) * 4 + i3]);
               }
         }
-        double* dst = my_partial + (int64_t)job * 64 * nblocks + b;
 #pragma unroll
         for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, (double)acc[e]);
+        }
       }
     }
     __syncthreads();  // everyone is done with `buf` before it is refilled
@@ -218,7 +309,7 @@ struct bsk_cplan {
 
 using namespace bsk;
 
-template <typename T, typename TC>
+template <typename T, typename TC, int PACKED>
 static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums, cudaStream_t st) {
   // tile size: double-buffered [nrows][tile_cells] must fit in shared memory
   const size_t budget = std::min<size_t>(cp->smem_limit, 227 * 1024) - 1024;
@@ -231,10 +322,10 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   const int ncta = (int)std::min<int64_t>(ntiles, cp->ncta_alloc);
   const size_t smem = 128 + 2 * (size_t)cp->nrows * tile * sizeof(T);
   const int64_t stride = (int64_t)njobs * 64 * cp->nblocks;
-  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T, TC>,
+  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T, TC, PACKED>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
-  tile_contract_kernel<T, TC><<<ncta, kThreads, smem, st>>>(
+  tile_contract_kernel<T, TC, PACKED><<<ncta, kThreads, smem, st>>>(
       (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, cp->split,
       njobs, cp->d_joboff, cp->d_partial, stride);
   count_launch();
@@ -375,9 +466,13 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
                            cudaMemcpyHostToDevice, st));
   BSK_CUDA(cudaMemcpyAsync(cp->d_joboff, cp->h_joboff, sizeof(int) * 3 * (size_t)njobs,
                            cudaMemcpyHostToDevice, st));
-  if (precision == BSK_F64) return contract_impl<double, double>(cp, ncells, njobs, sums, st);
-  return accum_precision == BSK_F64 ? contract_impl<float, double>(cp, ncells, njobs, sums, st)
-                                    : contract_impl<float, float>(cp, ncells, njobs, sums, st);
+  if (precision == BSK_F64) return contract_impl<double, double, 0>(cp, ncells, njobs, sums, st);
+  if (accum_precision == BSK_F64) return contract_impl<float, double, 0>(cp, ncells, njobs, sums, st);
+  static const char* mode = getenv("BSK_CONTRACT_MODE");   // A/B timing knob: 0 scalar, 1, 2 packed
+  const int m = mode ? atoi(mode) : 1;
+  if (m == 0) return contract_impl<float, float, 0>(cp, ncells, njobs, sums, st);
+  if (m == 1) return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
+  return contract_impl<float, float, 2>(cp, ncells, njobs, sums, st);
 }
 
 }  // extern "C"
