@@ -61,8 +61,13 @@ def _good_size(n, multiple):
             while r % f == 0:
                 r //= f
         if r == 1:
-            return m
+            break
         m += step
+    # a power of two within 15% is preferred: the pruned z-pass kernel handles those
+    p2 = 1 << (int(n) - 1).bit_length()
+    if p2 % step == 0 and p2 <= 1.15 * m:
+        return p2
+    return m
 
 
 def mode_of(j, k, n):
@@ -192,6 +197,9 @@ class NativeBackend:
             pass
 
     def set_compensation(self, tables):
+        if tables is None and not getattr(self, "_has_comp", False):
+            return                                   # already all ones: skip the upload + sync
+        self._has_comp = tables is not None
         cx, cy, cz = tables if tables is not None else (None, None, None)
         nat.check(self.lib.bsk_set_compensation(self.handle, nat.dptr(cx), nat.dptr(cy), nat.dptr(cz)),
                   "bsk_set_compensation")
@@ -285,8 +293,10 @@ class Engine:
 
     def __init__(self, grid: GridChoice, boxsize, precision=nat.F32, device=None, group=None,
                  backend_cls=NativeBackend, scratch_bytes=None, fft_precision=None,
-                 accum_precision=None, no_prune=False):
+                 accum_precision=None, no_prune=False, max_rows=None):
         self.grid = grid
+        self.max_rows = max_rows
+        self.last_batches = 0
         self.boxsize = box3(boxsize)
         self.precision = precision
         self.group = group
@@ -370,6 +380,25 @@ class Engine:
     def release_scratch(self):
         self._scratch = None
 
+    def row_capacity(self):
+        """How many shell fields ([ncells] of the storage dtype) fit in device memory next to
+        the synthesis scratch.  `max_rows` (tests) overrides the measurement."""
+        if self.max_rows is not None:
+            return int(self.max_rows)
+        if self.device.type != "cuda":
+            return 1 << 30
+        if getattr(self, "_row_cap", None) is not None:
+            return self._row_cap                     # measured once per engine (cudaMemGetInfo syncs)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        f = self.info
+        fft_item = 8 if self.cdtype == torch.complex64 else 16
+        scratch = 0 if self._scratch is not None else self.chunk * fft_item * (
+            f.xcols_complex_per_shell + f.planes2d_complex_per_shell)
+        avail = 0.92 * (free + cached) - scratch - (1 << 30)
+        self._row_cap = max(0, int(avail // (self.ncells * self.itemsize)))
+        return self._row_cap
+
     def synthesize(self, cube, kind, kpow, lo, hi, out):
         """Fill out[i] (i over bins) with the shell field of bin (lo[i], hi[i]).
         `out` is a [nbins][ncells] CUDA tensor (rows may be a view of a larger table)."""
@@ -421,10 +450,23 @@ def _pad4(n):
 FIELD_ROUTE = {1: (0, 0, 0), 2: (0, 0, 1), 3: (0, 1, 2)}  # which mesh feeds k1,k2,k3 (main.py:627-640)
 
 
+_UNIQ_CACHE = {}
+
+
 def _unique_triples(triples):
+    """Distinct index triples and the inverse map (cached: the same list is measured again for
+    every mesh / every step, and np.unique over rows costs milliseconds of idle GPU)."""
     triples = np.ascontiguousarray(np.asarray(triples, dtype=np.int64).reshape(-1, 3))
+    key = (triples.shape[0], hash(triples.tobytes()))
+    hit = _UNIQ_CACHE.get(key)
+    if hit is not None and np.array_equal(hit[0], triples):
+        return hit[1], hit[2]
     uniq, inverse = np.unique(triples, axis=0, return_inverse=True)
-    return uniq, np.asarray(inverse).reshape(-1)
+    inverse = np.asarray(inverse).reshape(-1)
+    if len(_UNIQ_CACHE) > 16:
+        _UNIQ_CACHE.clear()
+    _UNIQ_CACHE[key] = (triples.copy(), uniq, inverse)
+    return uniq, inverse
 
 
 def _mark(marks, name, engine):
@@ -433,6 +475,58 @@ def _mark(marks, name, engine):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream(engine.device))
         marks.append((name, ev))
+
+
+def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None):
+    """Evaluate every unique bin triple of `uniq` for each job.
+
+    The field table has `nseg` segments (one per source: mesh A/B/C, or unit / |k| shells) with
+    the same bin -> row layout; job j reads slot s from segment job_seg_off[j][s].  When all
+    needed shells fit in device memory this is one synthesis + one contraction pass; otherwise
+    the triangle list is cut (in order) into batches whose distinct bins fit, and the shells of
+    each batch are synthesised afresh — the memory-for-recompute trade of the reference's
+    "slow" path (bskit/main.py:1656-1661), but per batch instead of per triangle.
+    """
+    njobs = len(job_seg_off)
+    out = np.empty((njobs, len(uniq)))
+    seg_cap = max(4, (engine.row_capacity() // nseg) // 4 * 4)
+    if _pad4(int(uniq.max()) + 1) <= seg_cap or _pad4(len(np.unique(uniq))) <= seg_cap:
+        batches = [np.arange(len(uniq))]              # the common case: everything is resident
+    else:
+        batches, cur, cur_bins = [], [], set()
+        for t, tri in enumerate(uniq.tolist()):
+            new_bins = cur_bins.union(tri)
+            if cur and _pad4(len(new_bins)) > seg_cap:
+                batches.append(np.asarray(cur))
+                cur, new_bins = [], set(tri)
+            cur.append(t)
+            cur_bins = new_bins
+        if cur:
+            batches.append(np.asarray(cur))
+    for batch in batches:
+        tri = uniq[batch]
+        bins = np.unique(tri)
+        pos = np.full(int(bins.max()) + 1, -1, dtype=np.int64)
+        pos[bins] = np.arange(len(bins))
+        seg = _pad4(len(bins))
+        if seg > seg_cap and len(batch) > 0 and seg > 4:
+            raise MemoryError(f"a single triangle batch needs {nseg * seg} resident shell fields of "
+                              f"{engine.ncells * engine.itemsize / 2**30:.1f} GiB; only "
+                              f"{engine.row_capacity()} fit on this device")
+        table = torch.empty((nseg * seg, engine.ncells), dtype=engine.rdtype, device=engine.device)
+        for sidx in range(nseg):
+            for run in _runs(bins.tolist()):
+                r0 = sidx * seg + int(pos[run[0]])
+                synth(sidx, run, table[r0: r0 + len(run)])
+            for r in range(len(bins), seg):       # padding rows are read by the 4x4x4 blocks
+                table[sidx * seg + r].zero_()
+        _mark(marks, "shells_done", engine)
+        rows = pos[tri]
+        job_off = np.asarray(job_seg_off, dtype=np.int64) * seg
+        out[:, batch] = engine.contract(table, rows, job_off, marks=marks)
+        del table
+    engine.last_batches = len(batches)
+    return out
 
 
 def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None):
@@ -445,23 +539,11 @@ def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None):
     edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
     uniq, inverse = _unique_triples(triples)
     route = FIELD_ROUTE[len(cubes)]
-    narr = len(cubes)
-    sp = _pad4(len(edges))
-    table = torch.empty((narr * sp, engine.ncells), dtype=engine.rdtype, device=engine.device)
-    filled = np.zeros(narr * sp, dtype=bool)
-    for slot in range(3):
-        arr = route[slot]
-        need = np.unique(uniq[:, slot])
-        need = [int(b) for b in need if not filled[arr * sp + int(b)]]
-        for run in _runs(need):
-            engine.synthesize(cubes[arr], nat.KIND_DATA, 0.0, edges[run, 0], edges[run, 1],
-                              table[arr * sp + run[0]: arr * sp + run[-1] + 1])
-            filled[arr * sp + np.asarray(run)] = True
-    _fill_unused(table, filled)
-    rows = np.stack([uniq[:, s] + route[s] * sp for s in range(3)], axis=1)
-    _mark(marks, "shells_done", engine)
-    sums = engine.contract(table, rows, marks=marks)[0]
-    del table
+
+    def synth(sidx, run, out):
+        engine.synthesize(cubes[sidx], nat.KIND_DATA, 0.0, edges[run, 0], edges[run, 1], out)
+
+    sums = _batched_contract(engine, len(cubes), synth, [route], uniq, marks)[0]
     return sums[inverse] / float(engine.grid.neval) ** 3
 
 
@@ -470,22 +552,15 @@ def measure_grid_sums(engine: Engine, edges, triples, marks=None):
     (main.py:2006-2061): N_tri = sum n_a n_b n_c / M^3, k_1 = sum kappa_a n_b n_c / M^3 / N_tri ..."""
     edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
     uniq, inverse = _unique_triples(triples)
-    sp = _pad4(len(edges))
-    table = torch.empty((2 * sp, engine.ncells), dtype=engine.rdtype, device=engine.device)
-    filled = np.zeros(2 * sp, dtype=bool)
-    need = [int(b) for b in np.unique(uniq)]
-    for run in _runs(need):
-        engine.synthesize(None, nat.KIND_UNIT, 0.0, edges[run, 0], edges[run, 1],
-                          table[run[0]: run[-1] + 1])
-        engine.synthesize(None, nat.KIND_KPOW, 1.0, edges[run, 0], edges[run, 1],
-                          table[sp + run[0]: sp + run[-1] + 1])
-        filled[np.asarray(run)] = True
-        filled[sp + np.asarray(run)] = True
-    _fill_unused(table, filled)
-    jobs = ((0, 0, 0), (sp, 0, 0), (0, sp, 0), (0, 0, sp))
-    _mark(marks, "shells_done", engine)
-    sums = engine.contract(table, uniq, jobs, marks=marks) / float(engine.grid.neval) ** 3
-    del table
+
+    def synth(sidx, run, out):
+        if sidx == 0:
+            engine.synthesize(None, nat.KIND_UNIT, 0.0, edges[run, 0], edges[run, 1], out)
+        else:
+            engine.synthesize(None, nat.KIND_KPOW, 1.0, edges[run, 0], edges[run, 1], out)
+
+    jobs = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    sums = _batched_contract(engine, 2, synth, jobs, uniq, marks) / float(engine.grid.neval) ** 3
     ntri = np.rint(sums[0])                      # an exact triangle count (integer valued)
     with np.errstate(divide="ignore", invalid="ignore"):
         kmean = np.where(ntri[None, :] > 0, sums[1:4] / ntri[None, :], np.nan).T
@@ -503,10 +578,3 @@ def _runs(sorted_ids):
     if cur:
         runs.append(cur)
     return runs
-
-
-def _fill_unused(table, filled):
-    """Rows no triangle refers to are still read by the 4x4x4 blocks (their products are
-    discarded); give them finite contents."""
-    for r in np.flatnonzero(~filled).tolist():
-        table[r].zero_()

@@ -153,6 +153,7 @@ class _Measurer:
         else:
             self.precision = F32 if np.dtype(compute_dtype) == np.float32 else F64
         self._cubes = {}
+        self._grid_cache = {}
 
     def volume(self):
         return float(self.boxsize.prod())
@@ -179,8 +180,16 @@ class _Measurer:
         edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
         # N_tri and k_mean depend on (BoxSize, bins) only, not on Nmesh while 3 n_max < N
         # (SURVEY.md B.1), so the exact band-limited grid is always used here
-        e = self.session.engine(edges[:, 1].max(), F64, policy="auto" if self.session.grid_policy == "full" else None)
-        return self.session.eng.measure_grid_sums(e, edges, triples)
+        # The result is mesh independent, so it is cached per binning (the reference caches it
+        # in a file: step 1 of its 3-step workflow, usage.md:27-37).
+        triples = np.ascontiguousarray(np.asarray(triples, dtype=np.int64).reshape(-1, 3))
+        key = (edges.tobytes(), triples.tobytes())
+        if key not in self._grid_cache:
+            e = self.session.engine(edges[:, 1].max(), F64,
+                                    policy="auto" if self.session.grid_policy == "full" else None)
+            self._grid_cache = {key: self.session.eng.measure_grid_sums(e, edges, triples)}
+        ntri, kmean = self._grid_cache[key]
+        return ntri.copy(), kmean.copy()
 
 
 # --------------------------------------------------------------------------- #

@@ -338,3 +338,33 @@ def test_pruned_zpass_equals_generic_cufft_path(bk, syn, n, nb, prec):
     for i in (0, len(edges) // 2, len(edges) - 1):
         want = orc.data_shell(dk64, kk, edges[i, 0], edges[i, 1]).reshape(-1)
         assert np.abs(out[False][0][i] - want).max() / np.abs(want).max() < tol
+
+
+def test_memory_limited_batches_give_identical_results(bk, syn):
+    """When the shell fields do not fit in device memory the triangle list is processed in
+    batches with re-synthesis (engine._batched_contract); forced here with max_rows."""
+    import torch
+    from bskit_b200 import engine as eng, _native as nat
+    n, nb = 64, 12
+    kmin, kmax, dk = syn.bench_bins(nb)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    a = syn.lognormal_mesh(n, seed=1, dtype=np.float64)
+    b = syn.baryon_like_mesh(a, seed=2, dtype=np.float64)
+    g = eng.choose_grid(n, syn.BOX, edges[:, 1].max(), "full")
+    dev = torch.device("cuda", 0)
+    res = {}
+    for cap in (None, 16, 8):
+        e = eng.Engine(g, syn.BOX, nat.F64, device=dev, max_rows=cap)
+        cubes = [e.forward(a), e.forward(b)]
+        _, idx2 = orc.triangles_all(edges, 2)
+        res[cap] = (eng.measure_triangle_sums(e, cubes[:1], edges, idx),
+                    eng.measure_triangle_sums(e, cubes, edges, idx2),
+                    eng.measure_grid_sums(e, edges, idx), e.last_batches)
+        e.close()
+    assert res[None][3] == 1 and res[8][3] > 1
+    for cap in (16, 8):
+        np.testing.assert_allclose(res[cap][0], res[None][0], rtol=1e-12, atol=1e-14 * np.abs(res[None][0]).max())
+        np.testing.assert_allclose(res[cap][1], res[None][1], rtol=1e-12, atol=1e-14 * np.abs(res[None][1]).max())
+        assert np.array_equal(res[cap][2][0], res[None][2][0])
+        np.testing.assert_allclose(res[cap][2][1], res[None][2][1], rtol=1e-12)
