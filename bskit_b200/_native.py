@@ -20,7 +20,7 @@ MAX_CHUNK = 64
 EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
     "bsk_set_compensation", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
-    "bsk_shells", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_contract",
+    "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_contract",
     "bsk_launch_count",
 )
 
@@ -66,6 +66,7 @@ def lib():
     L.bsk_forward_local.argtypes = [vp, vp, ip, vp, vp, vp]
     L.bsk_forward_finish.argtypes = [vp, vp, vp]
     L.bsk_modes_per_bin.argtypes = [vp, ip, dp, dp, C.POINTER(C.c_int64)]
+    L.bsk_shells_prepare.argtypes = [vp, ip]
     L.bsk_shells.argtypes = [vp, vp, ip, C.c_double, ip, dp, dp, vp, vp, vp]
     L.bsk_cplan_create.argtypes = [C.POINTER(vp), ip, C.POINTER(C.c_int32), ip, ip]
     L.bsk_cplan_destroy.argtypes = [vp]

@@ -578,6 +578,15 @@ int bsk_modes_per_bin(bsk_plan* p, int nbins, const double* lo, const double* hi
   return BSK_OK;
 }
 
+int bsk_shells_prepare(bsk_plan* p, int nsh) {
+  BSK_REQUIRE(p && nsh >= 1 && nsh <= p->g.max_shells, "bsk_shells_prepare: bad argument");
+  cufftHandle h;
+  int rc;
+  if ((rc = get_invx(p, nsh, &h))) return rc;
+  if (p->use_zpass) return get_invy(p, nsh, &h);
+  return get_inv2d(p, nsh, &h);
+}
+
 int bsk_shells(bsk_plan* p, const void* cube, int kind, double kpow, int nsh, const double* lo,
                const double* hi, void* xcols, void* planes2d, void* fields) {
   BSK_REQUIRE(p && lo && hi && xcols && planes2d && fields, "bsk_shells: null argument");

@@ -45,7 +45,7 @@ __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }  // 1 pad 
 // One Stockham stage of radix R on the rows of this CTA.  TPR threads cooperate on a row.
 template <int R, int H, int TPR>
 __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, int p, bool active,
-                                               const double2* __restrict__ wtab /* e^{2 pi i j/(2H)} */) {
+                                               const cplx* __restrict__ wtab /* smem: e^{2 pi i j/(2H)} */) {
   constexpr int T = H / R;          // butterflies per row in this stage
   constexpr int PER = T / TPR;      // butterflies per thread (TPR = H/16, so PER = 16/R)
   cplx v[PER][R];
@@ -59,8 +59,7 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
     for (int m = 0; m < R; ++m) {
       cplx u = row[padidx(i + m * T)];
       if (m > 0 && p > 1) {
-        const double2 w = __ldg(&wtab[(2 * step * m) & (2 * H - 1)]);
-        u = zfft::cmul(u, cplx{w.x, w.y});
+        u = zfft::cmul(u, wtab[(2 * step * m) & (2 * H - 1)]);
       }
       v[b][m] = u;
     }
@@ -83,7 +82,7 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
 
 template <int H, int TPR, int P0, int REM>
 struct Stages {
-  static __device__ __forceinline__ void run(cplx* row, int lt, bool active, const double2* wtab) {
+  static __device__ __forceinline__ void run(cplx* row, int lt, bool active, const cplx* wtab) {
     constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
     stockham_stage<R, H, TPR>(row, lt, P0, active, wtab);
     if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, wtab);
@@ -102,9 +101,15 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
   constexpr int NT = RPC * TPR;                      // active threads
   constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1; // padded complex per row
   extern __shared__ __align__(16) unsigned char zsm[];
-  cplx* sm = reinterpret_cast<cplx*>(zsm);
+  cplx* wsm = reinterpret_cast<cplx*>(zsm);          // twiddle table e^{2 pi i j/M}, j < M
+  cplx* sm = wsm + M;                                // RPC padded rows
 
   const int tid = threadIdx.x;
+  for (int j = tid; j < M; j += blockDim.x) {
+    const double2 w = wtab[j];
+    wsm[j] = cplx{w.x, w.y};
+  }
+  __syncthreads();
   const int64_t groups_per_plane = M / RPC;
   const int64_t ngroups = planes * groups_per_plane;
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -127,9 +132,8 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
       // ---- pack the Hermitian half spectrum into a complex sequence of length H (in place)
       for (int k = lt; k <= H / 2; k += TPR) {
         const cplx xk = row[padidx(k)], xhk = row[padidx(H - k)];
-        const double2 w = __ldg(&wtab[k]);
         cplx zk, zhk;
-        zfft::pack_pair(xk, xhk, cplx{w.x, w.y}, zk, zhk);
+        zfft::pack_pair(xk, xhk, wsm[k], zk, zhk);
         row[padidx(k)] = zk;
         if (k != 0 && k != H - k) row[padidx(H - k)] = zhk;
       }
@@ -139,7 +143,7 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
     {
       const bool active = tid < NT;
       const int r = active ? tid / TPR : 0;
-      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, wtab);
+      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, wsm);
     }
     // ---- write the rows: x[2n] = Re z[n], x[2n+1] = Im z[n]; z[n] is stored at padidx(n)
     for (int e = tid; e < RPC * H; e += blockDim.x) {
@@ -161,7 +165,7 @@ static int launch_zpass(const void* ycols, void* fields, int Kz, int64_t planes,
   constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;
   constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;
   constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1;
-  const size_t smem = (size_t)RPC * ROWLEN * sizeof(cplx);
+  const size_t smem = ((size_t)RPC * ROWLEN + 2 * H) * sizeof(cplx);
   BSK_CUDA(cudaFuncSetAttribute(zpass_c2r_kernel<H, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   const int64_t ngroups = planes * (2 * H / RPC);

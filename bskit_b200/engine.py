@@ -234,6 +234,10 @@ class NativeBackend:
                   "bsk_modes_per_bin")
         return out
 
+    def prepare_shells(self, nsh):
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.bsk_shells_prepare(self.handle, int(nsh)), "bsk_shells_prepare")
+
     def shells(self, cube, kind, kpow, lo, hi, xcols, planes2d, fields_out):
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
@@ -242,12 +246,11 @@ class NativeBackend:
                                       xcols.data_ptr(), planes2d.data_ptr(), fields_out.data_ptr()),
                   "bsk_shells")
 
-    def contract(self, table, rows, ncells, job_off):
-        """table: [nrows][ncells] fields; rows: (T,3) int32 row triples into it.
-        Returns this rank's float64 sums [njobs][T] (CUDA tensor)."""
-        nrows = table.shape[0]
-        base, stride = table.data_ptr(), table.stride(0) * table.element_size()
-        row_ptrs = [base + r * stride for r in range(nrows)]
+    def contract(self, fields, rows, ncells, job_off):
+        """fields: list of 1-D field tensors (len % 4 == 0; entries may alias); rows: (T,3)
+        int32 triples of indices into it.  Returns this rank's float64 sums [njobs][T] (CUDA)."""
+        nrows = len(fields)
+        row_ptrs = [f.data_ptr() for f in fields]
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         job_off = np.ascontiguousarray(job_off, dtype=np.int32).reshape(-1, 3)
         njobs = len(job_off)
@@ -389,13 +392,13 @@ class Engine:
             return 1 << 30
         if getattr(self, "_row_cap", None) is not None:
             return self._row_cap                     # measured once per engine (cudaMemGetInfo syncs)
+        # allocate the synthesis scratch and the cuFFT work areas first, then see what is left
+        self._get_scratch(self.chunk)
+        self.backend.prepare_shells(self.chunk)
+        torch.cuda.synchronize(self.device)
         free, _ = torch.cuda.mem_get_info(self.device)
         cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-        f = self.info
-        fft_item = 8 if self.cdtype == torch.complex64 else 16
-        scratch = 0 if self._scratch is not None else self.chunk * fft_item * (
-            f.xcols_complex_per_shell + f.planes2d_complex_per_shell)
-        avail = 0.92 * (free + cached) - scratch - (1 << 30)
+        avail = 0.94 * (free + cached) - (1 << 30)
         self._row_cap = max(0, int(avail // (self.ncells * self.itemsize)))
         return self._row_cap
 
@@ -410,13 +413,16 @@ class Engine:
             self.backend.shells(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols, planes2d, out[s0:s1])
 
     # -- contraction ---------------------------------------------------------- #
-    def contract(self, table, rows, job_off=((0, 0, 0),), marks=None):
+    def contract(self, fields, rows, job_off=((0, 0, 0),), marks=None):
         """Triangle sums over this rank's cells, all-reduced over ranks.
 
-        table: [nrows][ncells] CUDA tensor of fields (nrows % 4 == 0);
-        rows: (T,3) row triples into `table`.  Returns float64 numpy [njobs][T].
+        fields: [nrows][ncells] tensor or a list of 1-D field tensors (nrows % 4 == 0; list
+        entries may alias, which is how padding rows cost no memory);
+        rows: (T,3) row triples into `fields`.  Returns float64 numpy [njobs][T].
         """
-        sums = self.backend.contract(table, rows, self.ncells, job_off)
+        if torch.is_tensor(fields):
+            fields = [fields[r] for r in range(fields.shape[0])]
+        sums = self.backend.contract(fields, rows, self.ncells, job_off)
         _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
@@ -425,6 +431,8 @@ class Engine:
     def close(self):
         self._scratch = None
         self.backend.close()
+        if self.device.type == "cuda":
+            torch.cuda.empty_cache()      # hand the (often multi-GB) scratch back to the driver
 
 
 def all_gather_concat(out, inp, group=None):
@@ -477,6 +485,24 @@ def _mark(marks, name, engine):
         marks.append((name, ev))
 
 
+def _alloc_table(shape, engine):
+    """Field table allocation; under memory pressure cached blocks of other sizes are released
+    first (the caching allocator cannot split a cached 96 GiB block into a 100 GiB request)."""
+    import os
+    if os.environ.get("BSK_DEBUG"):
+        free, tot = torch.cuda.mem_get_info(engine.device)
+        print(f"[bsk] table {shape} {engine.rdtype} = {shape[0]*shape[1]*engine.itemsize/2**30:.1f} GiB; free {free/2**30:.1f} "
+              f"reserved {torch.cuda.memory_reserved(engine.device)/2**30:.1f} allocated "
+              f"{torch.cuda.memory_allocated(engine.device)/2**30:.1f} rowcap {engine.row_capacity()}", flush=True)
+    try:
+        return torch.empty(shape, dtype=engine.rdtype, device=engine.device)
+    except torch.OutOfMemoryError:
+        pass
+    engine._row_cap = None
+    torch.cuda.empty_cache()
+    return torch.empty(shape, dtype=engine.rdtype, device=engine.device)
+
+
 def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None):
     """Evaluate every unique bin triple of `uniq` for each job.
 
@@ -489,14 +515,14 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
     """
     njobs = len(job_seg_off)
     out = np.empty((njobs, len(uniq)))
-    seg_cap = max(4, (engine.row_capacity() // nseg) // 4 * 4)
-    if _pad4(int(uniq.max()) + 1) <= seg_cap or _pad4(len(np.unique(uniq))) <= seg_cap:
+    seg_cap = max(1, engine.row_capacity() // nseg)       # distinct bins resident per segment
+    if int(uniq.max()) + 1 <= seg_cap or len(np.unique(uniq)) <= seg_cap:
         batches = [np.arange(len(uniq))]              # the common case: everything is resident
     else:
         batches, cur, cur_bins = [], [], set()
         for t, tri in enumerate(uniq.tolist()):
             new_bins = cur_bins.union(tri)
-            if cur and _pad4(len(new_bins)) > seg_cap:
+            if cur and len(new_bins) > seg_cap:
                 batches.append(np.asarray(cur))
                 cur, new_bins = [], set(tri)
             cur.append(t)
@@ -508,23 +534,26 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
         bins = np.unique(tri)
         pos = np.full(int(bins.max()) + 1, -1, dtype=np.int64)
         pos[bins] = np.arange(len(bins))
-        seg = _pad4(len(bins))
-        if seg > seg_cap and len(batch) > 0 and seg > 4:
-            raise MemoryError(f"a single triangle batch needs {nseg * seg} resident shell fields of "
-                              f"{engine.ncells * engine.itemsize / 2**30:.1f} GiB; only "
-                              f"{engine.row_capacity()} fit on this device")
-        table = torch.empty((nseg * seg, engine.ncells), dtype=engine.rdtype, device=engine.device)
+        nb = len(bins)
+        seg = _pad4(nb)
+        if nb > seg_cap:
+            raise MemoryError(f"one triangle needs {nseg * nb} resident shell fields of "
+                              f"{engine.ncells * engine.itemsize / 2**30:.1f} GiB each; only "
+                              f"{engine.row_capacity()} fit on this device (use grid='auto' or more GPUs)")
+        table = _alloc_table((nseg * nb, engine.ncells), engine)
+        fields = []
         for sidx in range(nseg):
             for run in _runs(bins.tolist()):
-                r0 = sidx * seg + int(pos[run[0]])
+                r0 = sidx * nb + int(pos[run[0]])
                 synth(sidx, run, table[r0: r0 + len(run)])
-            for r in range(len(bins), seg):       # padding rows are read by the 4x4x4 blocks
-                table[sidx * seg + r].zero_()
+            # the 4x4x4 blocks read rows in aligned groups of four: pad each segment's row list by
+            # repeating its first field (the products of padding rows are discarded)
+            fields += [table[sidx * nb + r] for r in range(nb)] + [table[sidx * nb]] * (seg - nb)
         _mark(marks, "shells_done", engine)
         rows = pos[tri]
         job_off = np.asarray(job_seg_off, dtype=np.int64) * seg
-        out[:, batch] = engine.contract(table, rows, job_off, marks=marks)
-        del table
+        out[:, batch] = engine.contract(fields, rows, job_off, marks=marks)
+        del table, fields
     engine.last_batches = len(batches)
     return out
 

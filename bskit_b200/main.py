@@ -306,10 +306,11 @@ def pk_FFT(mesh, kmin, kmax):
         for prec, kind, p in ((F64, nat.KIND_UNIT, 0.0), (F64, nat.KIND_KPOW, 0.5),
                               (meas.precision, nat.KIND_DATA, 0.0)):
             e = meas.session.engine(kmax, prec)
-            table = torch.ones((4, e.ncells), dtype=e.rdtype, device=e.device)
+            table = torch.ones((2, e.ncells), dtype=e.rdtype, device=e.device)
             cube = meas.cubes(e)[0] if kind == nat.KIND_DATA else None
             e.synthesize(cube, kind, p, lo, hi, table[0:1])
-            out.append(float(e.contract(table, rows)[0, 0]) / float(e.grid.neval) ** 3)
+            fields = [table[0], table[1], table[1], table[1]]
+            out.append(float(e.contract(fields, rows)[0, 0]) / float(e.grid.neval) ** 3)
         nbin = out[0]
         return out[2] * meas.volume() / nbin, nbin, out[1] / nbin
     finally:

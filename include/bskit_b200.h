@@ -135,6 +135,9 @@ int bsk_modes_per_bin(bsk_plan* plan, int nbins, const double* lo, const double*
  *   xcols    device scratch, nsh * xcols_complex_per_shell complex
  *   planes2d device scratch, nsh * planes2d_complex_per_shell complex
  *   fields   device out, [nsh][mxl*M*M] real (contiguous) */
+/* Create the cuFFT plans (and their work areas) a bsk_shells() call with nsh bins will use,
+ * so that the caller can size its field table from the memory that is really left. */
+int bsk_shells_prepare(bsk_plan* plan, int nsh);
 int bsk_shells(bsk_plan* plan, const void* cube, int kind, double kpow, int nsh,
                const double* lo, const double* hi, void* xcols, void* planes2d, void* fields);
 

@@ -35,6 +35,9 @@ class FakeBackend:
     def set_compensation(self, tables):
         self.comp = tables
 
+    def prepare_shells(self, nsh):
+        pass
+
     def forward_local(self, slab):
         n = self.grid.nmesh
         spec = np.fft.rfft2(slab.numpy().astype(np.float64), axes=(1, 2)) / float(n) ** 3
@@ -66,8 +69,8 @@ class FakeBackend:
             real = np.fft.irfft2(loc, s=(m, m), axes=(1, 2)) * float(m) ** 2
             fields_out[s].copy_(torch.from_numpy(real.reshape(-1)))
 
-    def contract(self, table, rows, ncells, job_off):
-        t = table.numpy()
+    def contract(self, fields, rows, ncells, job_off):
+        t = [f.numpy() for f in fields]
         out = np.zeros((len(job_off), len(rows)))
         for j, off in enumerate(np.asarray(job_off).reshape(-1, 3)):
             for i, (a, b, c) in enumerate(np.asarray(rows)):
