@@ -368,3 +368,70 @@ def test_memory_limited_batches_give_identical_results(bk, syn):
         np.testing.assert_allclose(res[cap][1], res[None][1], rtol=1e-12, atol=1e-14 * np.abs(res[None][1]).max())
         assert np.array_equal(res[cap][2][0], res[None][2][0])
         np.testing.assert_allclose(res[cap][2][1], res[None][2][1], rtol=1e-12)
+
+
+# --- BASELINE.json configs at full size (oracle on a sample of triangles) --------------- #
+def _ncores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def test_c2_256_lognormal_all_triangles_auto_plus_norm(bk, syn):
+    """configs[1]: 256^3 lognormal mesh, all triangles with dk = k_f (S=40, T=6730), auto +
+    normalisation.  Full list on the GPU; the float64 oracle on six triangles spread over it."""
+    n, nb = 256, 40
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.lognormal_mesh(n, seed=1, workers=_ncores())
+    edges = orc.bin_edges(kmin, kmax, dk)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="full")
+    assert len(fb.k_edges) == 6730
+    got = fb.measure_bispectrum_faster(0, 10 ** 9)
+    gi = fb.measure_gridinfo_faster(0, 10 ** 9)
+    fb.close()
+    fa = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="auto")
+    ga = fa.measure_bispectrum_faster(0, 10 ** 9)
+    fa.close()
+    assert_b_close(ga["B"], got["B"])                       # band-limited == mesh grid, all 6730
+    idx = np.asarray(fb.k_indices)
+    pick = np.linspace(0, len(idx) - 1, 6).astype(int)
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx[pick], workers=_ncores())
+    rms = np.sqrt(np.mean(got["B"] ** 2))
+    assert np.all(np.abs(got["B"][pick] - want) <= RTOL_B * np.abs(want) + 1e-6 * rms)
+    wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx[pick], workers=_ncores())
+    assert np.array_equal(gi["N_tri"][pick], np.rint(wn))
+    np.testing.assert_allclose(gi["k_mean"][pick], wk, rtol=1e-9)
+    assert np.all(gi["N_tri"] == np.rint(gi["N_tri"])) and gi["N_tri"].min() > 0
+    # exact integer mode counts of every k-bin
+    from bskit_b200 import engine as eng, _native as nat
+    import torch
+    e = eng.Engine(eng.choose_grid(n, syn.BOX, edges[:, 1].max(), "full"), syn.BOX, nat.F64,
+                   device=torch.device("cuda", 0))
+    assert np.array_equal(e.backend.modes_per_bin(edges[:, 0], edges[:, 1]),
+                          orc.modes_per_bin(n, syn.BOX, edges))
+    e.close()
+
+
+def test_c3_512_isosceles_and_squeezed_cross(bk, syn):
+    """configs[2]: 512^3, isosceles m=2 and squeezed-isosceles bins (S=80), matter x baryon
+    <AAB> cross-bispectrum.  Full lists on the GPU; oracle on three triangles of each list."""
+    n, nb = 512, 80
+    kmin, kmax, dk = syn.bench_bins(nb)
+    a = syn.lognormal_mesh(n, seed=1, workers=_ncores())
+    b = syn.baryon_like_mesh(a, seed=2, workers=_ncores())
+    edges = orc.bin_edges(kmin, kmax, dk)
+    dk_a = orc.forward(a.astype(np.float64), _ncores())
+    dk_b = orc.forward(b.astype(np.float64), _ncores())
+    for kw, (e6, idx), ntri in ((dict(triangle_type="isosceles", isos_mult=2.0), orc.triangles_isosceles(edges, 2.0), 74),
+                                (dict(triangle_type="squeezed", squeezed_bin_index=0), orc.triangles_squeezed(edges, 0), 79)):
+        assert len(idx) == ntri                                     # SURVEY 8a / 8d table
+        fb = bk.FFTBispectrum(a, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, second=b, grid="full", **kw)
+        assert np.array_equal(fb.k_indices, idx) and np.array_equal(fb.k_edges, e6)
+        got = fb.measure_bispectrum_faster(0, 10 ** 9)["B"]
+        fb.close()
+        fa = bk.FFTBispectrum(a, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, second=b, grid="auto", **kw)
+        assert_b_close(fa.measure_bispectrum_faster(0, 10 ** 9)["B"], got)
+        fa.close()
+        pick = np.array([1, len(idx) // 2, len(idx) - 1])
+        want = orc.measure_unnormalized(None, syn.BOX, edges, idx[pick], workers=_ncores(),
+                                        delta_k=[dk_a, dk_b])
+        rms = np.sqrt(np.mean(got ** 2))
+        assert np.all(np.abs(got[pick] - want) <= RTOL_B * np.abs(want) + 1e-6 * rms), (got[pick], want)
