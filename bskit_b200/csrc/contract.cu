@@ -83,18 +83,111 @@ template <> struct Vec<double> {
   }
 };
 
-// T: storage type of the fields; TC: type of the products and per-tile accumulators.
-// PACKED (float/float only): two cells per instruction with Blackwell's packed FP32 math
-// (FMUL2 / FFMA2, fma.rn.f32x2): the (x,y) and (z,w) halves of each 128-bit shared-memory load
-// are already aligned register pairs, so the inner loop issues half as many instructions for the
-// same FMA-pipe work and keeps two partial sums (even / odd cells) per accumulator.
+// Accumulator element: PACKED keeps (even-cell sum, odd-cell sum) pairs for FFMA2.
+template <typename TC, int PACKED> struct AccOf { using type = TC; };
+template <> struct AccOf<float, 1> { using type = float2; };
+
+template <typename A> __device__ __forceinline__ void acc_zero(A (&acc)[64]);
+template <> __device__ __forceinline__ void acc_zero<float>(float (&acc)[64]) {
+#pragma unroll
+  for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+}
+template <> __device__ __forceinline__ void acc_zero<double>(double (&acc)[64]) {
+#pragma unroll
+  for (int e = 0; e < 64; ++e) acc[e] = 0.0;
+}
+template <> __device__ __forceinline__ void acc_zero<float2>(float2 (&acc)[64]) {
+#pragma unroll
+  for (int e = 0; e < 64; ++e) acc[e] = make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ double acc_value(float v) { return (double)v; }
+__device__ __forceinline__ double acc_value(double v) { return v; }
+__device__ __forceinline__ double acc_value(float2 v) { return (double)v.x + (double)v.y; }
+
+// Add the n vectors [0,n) of three groups of four rows into the 4x4x4 accumulators.
+// PACKED (float only): two cells per instruction with Blackwell's packed FP32 math (FMUL2 /
+// FFMA2, fma.rn.f32x2): the (x,y) and (z,w) halves of each 128-bit shared-memory load are
+// already aligned register pairs, so the loop issues half as many instructions for the same
+// FMA-pipe work.  The cell order is rotated per lane so that lanes reading different rows hit
+// different banks.
 template <typename T, typename TC, int PACKED>
+__device__ __forceinline__ void accumulate_slice(typename AccOf<TC, PACKED>::type (&acc)[64],
+                                                 const typename Vec<T>::type* __restrict__ pa,
+                                                 const typename Vec<T>::type* __restrict__ pb,
+                                                 const typename Vec<T>::type* __restrict__ pc, int n,
+                                                 int rot, int rowstride_v) {
+  constexpr int W = Vec<T>::W;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    int q = i + rot;
+    if (q >= n) q -= n;
+    if constexpr (PACKED == 1) {
+      float4 va[4], vb[4], vc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        va[r] = pa[(size_t)r * rowstride_v + q];
+        vb[r] = pb[(size_t)r * rowstride_v + q];
+        vc[r] = pc[(size_t)r * rowstride_v + q];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 a2[4], b2[4], c2[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a2[r] = h ? make_float2(va[r].z, va[r].w) : make_float2(va[r].x, va[r].y);
+          b2[r] = h ? make_float2(vb[r].z, vb[r].w) : make_float2(vb[r].x, vb[r].y);
+          c2[r] = h ? make_float2(vc[r].z, vc[r].w) : make_float2(vc[r].x, vc[r].y);
+        }
+#pragma unroll
+        for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const float2 pr = __fmul2_rn(a2[i1], b2[i2]);
+#pragma unroll
+            for (int i3 = 0; i3 < 4; ++i3)
+              acc[(i1 * 4 + i2) * 4 + i3] = __ffma2_rn(pr, c2[i3], acc[(i1 * 4 + i2) * 4 + i3]);
+          }
+      }
+    } else {
+      TC a[4][W], bb[4][W], c[4][W];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        Vec<T>::unpack(pa[(size_t)r * rowstride_v + q], a[r]);
+        Vec<T>::unpack(pb[(size_t)r * rowstride_v + q], bb[r]);
+        Vec<T>::unpack(pc[(size_t)r * rowstride_v + q], c[r]);
+      }
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+#pragma unroll
+        for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const TC pr = a[i1][w] * bb[i2][w];
+#pragma unroll
+            for (int i3 = 0; i3 < 4; ++i3)
+              acc[(i1 * 4 + i2) * 4 + i3] = fma(pr, c[i3][w], acc[(i1 * 4 + i2) * 4 + i3]);
+          }
+    }
+  }
+}
+
+// T: storage type of the fields; TC: type of the products and per-tile accumulators.
+// Two schedules share the code:
+//  * dense lists (units = blocks x split > CTA size, or several jobs): each thread walks its
+//    units per tile, zeroing the accumulators before and reducing them into the float64
+//    partials after every (unit, job);
+//  * sparse lists (units <= CTA size, one job — equilateral / squeezed / isosceles lists, where
+//    the kernel is HBM-bound): a thread keeps ONE unit's accumulators in registers across tiles
+//    and reduces them every `flush_every` tiles, so the float64 reductions do not outnumber
+//    the loads.
+template <typename T, typename TC, int PACKED, bool PERSIST>
 __global__ void __launch_bounds__(kThreads, 1)
 tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
                      const int4* __restrict__ blocks, int nblocks, int split, int njobs,
                      const int* __restrict__ joboff, double* __restrict__ partial,
-                     int64_t partial_stride) {
+                     int64_t partial_stride, int flush_every) {
   using V = typename Vec<T>::type;
+  using A = typename AccOf<TC, PACKED>::type;
   constexpr int W = Vec<T>::W;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // 2 mbarriers
@@ -129,6 +222,16 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
   double* my_partial = partial + (int64_t)blockIdx.x * partial_stride;
   const int units = nblocks * split;
   const int rowstride_v = tile_cells / W;
+  constexpr bool persist = PERSIST;  // host guarantees units <= kThreads && njobs == 1
+
+  A acc[64];
+  acc_zero(acc);
+  int since_flush = 0;
+  // persistent schedule: this thread's unit is fixed
+  const int pb_ = tid < units ? tid % nblocks : 0;
+  const int pg_ = tid < units ? tid / nblocks : 0;
+  const int4 pblk = blocks[pb_];
+  const int j0 = joboff[0], j1 = joboff[1], j2 = joboff[2];
 
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
@@ -142,137 +245,52 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
     const int nq = len / W;
     const V* tv = reinterpret_cast<const V*>(tiles + (size_t)buf * buf_elems);
 
-    for (int u = tid; u < units; u += kThreads) {
-      const int b = u % nblocks;
-      const int g = u / nblocks;
-      const int q0 = (int)(((int64_t)nq * g) / split);
-      const int q1 = (int)(((int64_t)nq * (g + 1)) / split);
-      const int n = q1 - q0;
-      if (n <= 0) continue;
-      const int4 blk = blocks[b];
-      const int rot = lane % n;
-      for (int job = 0; job < njobs; ++job) {
-        const V* pa = tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0;
-        const V* pb = tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0;
-        const V* pc = tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0;
-        double* dst = my_partial + (int64_t)job * 64 * nblocks + b;
-        if constexpr (PACKED == 2) {
-          // 64-bit loads (2 cells), operands of the next step prefetched while this one computes
-          float2 acc2[64];
+    if constexpr (persist) {
+      if (tid < units) {
+        const int q0 = (int)(((int64_t)nq * pg_) / split);
+        const int q1 = (int)(((int64_t)nq * (pg_ + 1)) / split);
+        const int n = q1 - q0;
+        if (n > 0)
+          accumulate_slice<T, TC, PACKED>(acc, tv + (size_t)(pblk.x + j0) * rowstride_v + q0,
+                                          tv + (size_t)(pblk.y + j1) * rowstride_v + q0,
+                                          tv + (size_t)(pblk.z + j2) * rowstride_v + q0, n, lane % n,
+                                          rowstride_v);
+        if (++since_flush == flush_every) {
+          double* dst = my_partial + pb_;
 #pragma unroll
-          for (int e = 0; e < 64; ++e) acc2[e] = make_float2(0.f, 0.f);
-          const float2* ha = reinterpret_cast<const float2*>(pa);
-          const float2* hb = reinterpret_cast<const float2*>(pb);
-          const float2* hc = reinterpret_cast<const float2*>(pc);
-          const int n2 = 2 * n, rs2 = 2 * rowstride_v;
-          int q = lane % n2;
-          float2 a2[4], b2[4], c2[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            a2[r] = ha[(size_t)r * rs2 + q];
-            b2[r] = hb[(size_t)r * rs2 + q];
-            c2[r] = hc[(size_t)r * rs2 + q];
-          }
-#pragma unroll 1
-          for (int i = 0; i < n2; ++i) {
-            q = q + 1 == n2 ? 0 : q + 1;
-            float2 na[4], nb[4], nc[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {      // one step ahead (the last prefetch is unused)
-              na[r] = ha[(size_t)r * rs2 + q];
-              nb[r] = hb[(size_t)r * rs2 + q];
-              nc[r] = hc[(size_t)r * rs2 + q];
-            }
-#pragma unroll
-            for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const float2 pr = __fmul2_rn(a2[i1], b2[i2]);
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3)
-                  acc2[(i1 * 4 + i2) * 4 + i3] = __ffma2_rn(pr, c2[i3], acc2[(i1 * 4 + i2) * 4 + i3]);
-              }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              a2[r] = na[r];
-              b2[r] = nb[r];
-              c2[r] = nc[r];
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 64; ++e)
-            atomicAdd(dst + (int64_t)e * nblocks, (double)acc2[e].x + (double)acc2[e].y);
-        } else if constexpr (PACKED == 1) {
-          float2 acc2[64];
-#pragma unroll
-          for (int e = 0; e < 64; ++e) acc2[e] = make_float2(0.f, 0.f);
-#pragma unroll 1
-          for (int i = 0; i < n; ++i) {
-            int q = i + rot;
-            if (q >= n) q -= n;
-            float4 va[4], vb[4], vc[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              va[r] = pa[(size_t)r * rowstride_v + q];
-              vb[r] = pb[(size_t)r * rowstride_v + q];
-              vc[r] = pc[(size_t)r * rowstride_v + q];
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float2 a2[4], b2[4], c2[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                a2[r] = h ? make_float2(va[r].z, va[r].w) : make_float2(va[r].x, va[r].y);
-                b2[r] = h ? make_float2(vb[r].z, vb[r].w) : make_float2(vb[r].x, vb[r].y);
-                c2[r] = h ? make_float2(vc[r].z, vc[r].w) : make_float2(vc[r].x, vc[r].y);
-              }
-#pragma unroll
-              for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-                for (int i2 = 0; i2 < 4; ++i2) {
-                  const float2 pr = __fmul2_rn(a2[i1], b2[i2]);
-#pragma unroll
-                  for (int i3 = 0; i3 < 4; ++i3)
-                    acc2[(i1 * 4 + i2) * 4 + i3] = __ffma2_rn(pr, c2[i3], acc2[(i1 * 4 + i2) * 4 + i3]);
-                }
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 64; ++e)
-            atomicAdd(dst + (int64_t)e * nblocks, (double)acc2[e].x + (double)acc2[e].y);
-        } else {
-        TC acc[64];
-#pragma unroll
-        for (int e = 0; e < 64; ++e) acc[e] = (TC)0;
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) {
-          int q = i + rot;
-          if (q >= n) q -= n;
-          TC a[4][W], bb[4][W], c[4][W];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            Vec<T>::unpack(pa[(size_t)r * rowstride_v + q], a[r]);
-            Vec<T>::unpack(pb[(size_t)r * rowstride_v + q], bb[r]);
-            Vec<T>::unpack(pc[(size_t)r * rowstride_v + q], c[r]);
-          }
-#pragma unroll
-          for (int w = 0; w < W; ++w)
-#pragma unroll
-            for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const TC pr = a[i1][w] * bb[i2][w];
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3)
-                  acc[(i1 * 4 + i2) * 4 + i3] = fma(pr, c[i3][w], acc[(i1 * 4 + i2) * 4 + i3]);
-              }
+          for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, acc_value(acc[e]));
+          acc_zero(acc);
+          since_flush = 0;
         }
+      }
+    } else {
+      for (int u = tid; u < units; u += kThreads) {
+        const int b = u % nblocks;
+        const int g = u / nblocks;
+        const int q0 = (int)(((int64_t)nq * g) / split);
+        const int q1 = (int)(((int64_t)nq * (g + 1)) / split);
+        const int n = q1 - q0;
+        if (n <= 0) continue;
+        const int4 blk = blocks[b];
+        const int rot = lane % n;
+        for (int job = 0; job < njobs; ++job) {
+          acc_zero(acc);
+          accumulate_slice<T, TC, PACKED>(
+              acc, tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0,
+              tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0,
+              tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0, n, rot, rowstride_v);
+          double* dst = my_partial + (int64_t)job * 64 * nblocks + b;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, (double)acc[e]);
+          for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, acc_value(acc[e]));
         }
       }
     }
     __syncthreads();  // everyone is done with `buf` before it is refilled
+  }
+  if (persist && tid < units && since_flush > 0) {
+    double* dst = my_partial + pb_;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) atomicAdd(dst + (int64_t)e * nblocks, acc_value(acc[e]));
   }
 }
 
@@ -316,7 +334,7 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   // tile size: double-buffered [nrows][tile_cells] must fit in shared memory
   const size_t budget = std::min<size_t>(cp->smem_limit, 227 * 1024) - 1024;
   int tile = (int)(budget / (2 * (size_t)cp->nrows * sizeof(T)));
-  tile = std::min(tile, 1024);
+  tile = std::min(tile, 8192);   // few rows -> long tiles: keeps >= 100 KB in flight per SM
   tile -= tile % 32;
   BSK_REQUIRE(tile >= 32, "bsk_contract: %d rows do not fit in shared memory; split the row set",
               cp->nrows);
@@ -324,12 +342,17 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   const int ncta = (int)std::min<int64_t>(ntiles, cp->ncta_alloc);
   const size_t smem = 128 + 2 * (size_t)cp->nrows * tile * sizeof(T);
   const int64_t stride = (int64_t)njobs * 64 * cp->nblocks;
-  BSK_CUDA(cudaFuncSetAttribute(tile_contract_kernel<T, TC, PACKED>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool persist = (cp->nblocks * cp->split <= kThreads) && njobs == 1;
+  // the sparse-list schedule is HBM-bound: it uses the scalar (spill-free) inner loop
+  auto kern = persist ? tile_contract_kernel<T, TC, 0, true>
+                      : tile_contract_kernel<T, TC, PACKED, false>;
+  BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
-  tile_contract_kernel<T, TC, PACKED><<<ncta, kThreads, smem, st>>>(
+  // sparse-list schedule: reduce into float64 after ~1024 cells per thread
+  const int flush_every = std::max(1, (1024 * cp->split) / tile);
+  kern<<<ncta, kThreads, smem, st>>>(
       (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, cp->split,
-      njobs, cp->d_joboff, cp->d_partial, stride);
+      njobs, cp->d_joboff, cp->d_partial, stride, flush_every);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   const int64_t total = (int64_t)njobs * cp->ntri;
@@ -384,7 +407,8 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
   // split each block's tile over `split` threads so that a round fills the CTA
   int best = 1;
   double best_eff = 0.0;
-  for (int g = 1; g <= 8; ++g) {
+  const int gmax = cp->nblocks * 8 <= kThreads ? kThreads / cp->nblocks : 8;
+  for (int g = 1; g <= gmax; ++g) {
     const int units = cp->nblocks * g;
     const int rounds = (units + kThreads - 1) / kThreads;
     const double eff = (double)units / ((double)rounds * kThreads);
@@ -479,11 +503,10 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
   }
   if (precision == BSK_F64) return contract_impl<double, double, 0>(cp, ncells, njobs, sums, st);
   if (accum_precision == BSK_F64) return contract_impl<float, double, 0>(cp, ncells, njobs, sums, st);
-  static const char* mode = getenv("BSK_CONTRACT_MODE");   // A/B timing knob: 0 scalar, 1, 2 packed
+  static const char* mode = getenv("BSK_CONTRACT_MODE");   // A/B timing knob: 0 scalar FFMA, 1 packed FFMA2
   const int m = mode ? atoi(mode) : 1;
   if (m == 0) return contract_impl<float, float, 0>(cp, ncells, njobs, sums, st);
-  if (m == 1) return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
-  return contract_impl<float, float, 2>(cp, ncells, njobs, sums, st);
+  return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
 }
 
 }  // extern "C"

@@ -399,7 +399,12 @@ class Engine:
         free, _ = torch.cuda.mem_get_info(self.device)
         cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
         avail = 0.94 * (free + cached) - (1 << 30)
-        self._row_cap = max(0, int(avail // (self.ncells * self.itemsize)))
+        cap = max(0, int(avail // (self.ncells * self.itemsize)))
+        if self.world > 1:      # every rank must cut the triangle list into the same batches
+            t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            cap = int(t.item())
+        self._row_cap = cap
         return self._row_cap
 
     def synthesize(self, cube, kind, kpow, lo, hi, out):
