@@ -46,7 +46,7 @@ __all__ = [
     "generate_triangle_bin_list",
     "number_field", "k_field", "pk_FFT", "compute_Nbin", "compute_k_means_on_grid",
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
-    "combine_gridinfo_and_unnormalized",
+    "combine_gridinfo_and_unnormalized", "clear_cache",
 ]
 
 F32, F64 = 0, 1
@@ -95,6 +95,42 @@ class _Session:
 
 
 _sessions = {}
+_SHARED = {}            # (nmesh, box, grid, device, group, fft, accum) -> [session, refcount]
+_SHARED_MAX = 4
+
+
+def _acquire_session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype):
+    """Sessions (cuFFT plans, contraction schedules, scratch) are shared between
+    FFTBispectrum objects with the same geometry: a pipeline over many snapshots pays for
+    plan creation once.  `clear_cache()` releases them."""
+    key = (int(nmesh), tuple(np.asarray(boxsize, dtype=np.float64).tolist()), str(grid), str(device),
+           id(group) if group is not None else None,
+           None if fft_dtype is None else np.dtype(fft_dtype).name,
+           None if accum_dtype is None else np.dtype(accum_dtype).name)
+    ent = _SHARED.get(key)
+    if ent is None:
+        if len(_SHARED) >= _SHARED_MAX:          # drop idle sessions, oldest first
+            for k in [k for k, v in _SHARED.items() if v[1] <= 0][:len(_SHARED) - _SHARED_MAX + 1]:
+                _SHARED.pop(k)[0].close()
+        ent = [_Session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype), 0]
+        _SHARED[key] = ent
+    ent[1] += 1
+    return key, ent[0]
+
+
+def _release_session(key):
+    ent = _SHARED.get(key)
+    if ent is not None:
+        ent[1] -= 1
+
+
+def clear_cache():
+    """Destroy every cached session (plans, schedules, scratch buffers) that is not in use."""
+    for k in [k for k, v in _SHARED.items() if v[1] <= 0]:
+        _SHARED.pop(k)[0].close()
+    for s in list(_sessions.values()):
+        s.close()
+    _sessions.clear()
 
 
 def _session_for(box_size, n_mesh):
@@ -146,7 +182,8 @@ class _Measurer:
         self.meshes = meshes
         self.nmesh = int(first.attrs["Nmesh"][0])
         self.boxsize = np.asarray(first.attrs["BoxSize"], dtype=np.float64)
-        self.session = _Session(self.nmesh, self.boxsize, grid, device, group, fft_dtype, accum_dtype)
+        self._session_key, self.session = _acquire_session(self.nmesh, self.boxsize, grid, device,
+                                                           group, fft_dtype, accum_dtype)
         if compute_dtype is None:
             # the reference computes in the mesh's own dtype (f4 meshes -> f4 fields)
             self.precision = F32 if all(_mesh_dtype_code(m) == F32 for m in meshes) else F64
@@ -154,6 +191,13 @@ class _Measurer:
             self.precision = F32 if np.dtype(compute_dtype) == np.float32 else F64
         self._cubes = {}
         self._grid_cache = {}
+
+    def release(self):
+        """Drop this object's spectra; the shared session stays cached for the next object."""
+        self._cubes = {}
+        if self._session_key is not None:
+            _release_session(self._session_key)
+            self._session_key = None
 
     def volume(self):
         return float(self.boxsize.prod())
@@ -257,7 +301,7 @@ def compute_bk_FFT_value(mesh, bins, Nbin=1, verbose=0, second_mesh=None, third_
     try:
         return float(meas.unnormalized(edges, triples)[0] / Nbin)
     finally:
-        meas.session.close()
+        meas.release()
 
 
 def bk_FFT_unnormalized_value(mesh, bin0, bin1, bin2, verbose=0, second_mesh=None, third_mesh=None):
@@ -314,7 +358,7 @@ def pk_FFT(mesh, kmin, kmax):
         nbin = out[0]
         return out[2] * meas.volume() / nbin, nbin, out[1] / nbin
     finally:
-        meas.session.close()
+        meas.release()
 
 
 def combine_gridinfo_and_unnormalized(bin_info, b_vals, k_max=np.inf, tol=0.01):
@@ -602,7 +646,9 @@ class FFTBispectrum:
             np.savetxt(out_file, table, header=header)
 
     def close(self):
-        """Release GPU plans and buffers held by this object."""
+        """Release this object's GPU spectra.  Plans, schedules and scratch stay in the
+        module-level session cache for the next object of the same geometry; call
+        ``bskit_b200.clear_cache()`` to free those too."""
         if self._measurer is not None:
-            self._measurer.session.close()
+            self._measurer.release()
             self._measurer = None
