@@ -43,8 +43,11 @@ __global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __r
 __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }  // 1 pad per 16 complex
 
 // One Stockham stage of radix R on the rows of this CTA.  TPR threads cooperate on a row.
+// In the first stage (p == 1) only packed entries with index < Kz or > H-Kz can be non-zero
+// (the rest were never written): they are taken as zero without touching shared memory.
 template <int R, int H, int TPR>
 __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, int p, bool active,
+                                               int Kz,
                                                const cplx* __restrict__ wtab /* smem: e^{2 pi i j/(2H)} */) {
   constexpr int T = H / R;          // butterflies per row in this stage
   constexpr int PER = T / TPR;      // butterflies per thread (TPR = H/16, so PER = 16/R)
@@ -57,7 +60,9 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
     const int step = (H / (p * R)) * k;  // twiddle e^{2 pi i k m/(pR)} = wtab[2*step*m]
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-      cplx u = row[padidx(i + m * T)];
+      const int idx = i + m * T;
+      cplx u{0.0, 0.0};
+      if (p > 1 || idx < Kz || idx > H - Kz) u = row[padidx(idx)];
       if (m > 0 && p > 1) {
         u = zfft::cmul(u, wtab[(2 * step * m) & (2 * H - 1)]);
       }
@@ -82,10 +87,11 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
 
 template <int H, int TPR, int P0, int REM>
 struct Stages {
-  static __device__ __forceinline__ void run(cplx* row, int lt, bool active, const cplx* wtab) {
+  static __device__ __forceinline__ void run(cplx* row, int lt, bool active, int Kz,
+                                             const cplx* wtab) {
     constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
-    stockham_stage<R, H, TPR>(row, lt, P0, active, wtab);
-    if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, wtab);
+    stockham_stage<R, H, TPR>(row, lt, P0, active, Kz, wtab);
+    if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, Kz, wtab);
   }
 };
 
@@ -115,15 +121,11 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int64_t plane = grp / groups_per_plane;
     const int y0 = (int)(grp - plane * groups_per_plane) * RPC;
-    // ---- load the kept coefficients: X[kz] for kz < Kz, zero elsewhere (incl. index H)
-    for (int e = tid; e < RPC * (H + 1); e += blockDim.x) {
+    // ---- load the kept coefficients X[kz], kz < Kz (entries >= Kz are implicitly zero)
+    for (int e = tid; e < RPC * Kz; e += blockDim.x) {
       const int r = e % RPC, kz = e / RPC;
-      cplx v{0.0, 0.0};
-      if (kz < Kz) {
-        const double2 g = ycols[((int64_t)plane * Kz + kz) * M + y0 + r];
-        v = cplx{g.x, g.y};
-      }
-      sm[r * ROWLEN + padidx(kz)] = v;
+      const double2 g = ycols[((int64_t)plane * Kz + kz) * M + y0 + r];
+      sm[r * ROWLEN + padidx(kz)] = cplx{g.x, g.y};
     }
     __syncthreads();
     if (tid < NT) {
@@ -131,7 +133,10 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
       cplx* row = sm + r * ROWLEN;
       // ---- pack the Hermitian half spectrum into a complex sequence of length H (in place)
       for (int k = lt; k <= H / 2; k += TPR) {
-        const cplx xk = row[padidx(k)], xhk = row[padidx(H - k)];
+        if (k >= Kz && H - k >= Kz) continue;         // both inputs zero -> both outputs zero
+        const cplx zero{0.0, 0.0};
+        const cplx xk = k < Kz ? row[padidx(k)] : zero;
+        const cplx xhk = H - k < Kz ? row[padidx(H - k)] : zero;
         cplx zk, zhk;
         zfft::pack_pair(xk, xhk, wsm[k], zk, zhk);
         row[padidx(k)] = zk;
@@ -143,7 +148,7 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
     {
       const bool active = tid < NT;
       const int r = active ? tid / TPR : 0;
-      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, wsm);
+      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, Kz, wsm);
     }
     // ---- write the rows: x[2n] = Re z[n], x[2n+1] = Im z[n]; z[n] is stored at padidx(n)
     for (int e = tid; e < RPC * H; e += blockDim.x) {
