@@ -48,7 +48,7 @@ __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }  // 1 pad 
 template <int R, int H, int TPR>
 __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, int p, bool active,
                                                int Kz,
-                                               const cplx* __restrict__ wtab /* smem: e^{2 pi i j/(2H)} */) {
+                                               const cplx* __restrict__ tw /* smem [R][p]: e^{2 pi i k m/(pR)} */) {
   constexpr int T = H / R;          // butterflies per row in this stage
   constexpr int PER = T / TPR;      // butterflies per thread (TPR = H/16, so PER = 16/R)
   cplx v[PER][R];
@@ -57,14 +57,13 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
   for (int b = 0; b < PER; ++b) {
     const int i = lt + b * TPR;
     const int k = i & (p - 1);
-    const int step = (H / (p * R)) * k;  // twiddle e^{2 pi i k m/(pR)} = wtab[2*step*m]
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int idx = i + m * T;
       cplx u{0.0, 0.0};
       if (p > 1 || idx < Kz || idx > H - Kz) u = row[padidx(idx)];
       if (m > 0 && p > 1) {
-        u = zfft::cmul(u, wtab[(2 * step * m) & (2 * H - 1)]);
+        u = zfft::cmul(u, tw[m * p + k]);   // lanes with consecutive k: conflict-free
       }
       v[b][m] = u;
     }
@@ -87,11 +86,22 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
 
 template <int H, int TPR, int P0, int REM>
 struct Stages {
+  static constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
+  // per-stage twiddle tables are stored back to back: [R][P0] entries each
   static __device__ __forceinline__ void run(cplx* row, int lt, bool active, int Kz,
-                                             const cplx* wtab) {
-    constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
-    stockham_stage<R, H, TPR>(row, lt, P0, active, Kz, wtab);
-    if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, Kz, wtab);
+                                             const cplx* tw) {
+    stockham_stage<R, H, TPR>(row, lt, P0, active, Kz, tw);
+    if constexpr (REM / R > 1)
+      Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, Kz, tw + R * P0);
+  }
+  static __device__ __forceinline__ void fill(cplx* tw, const double2* __restrict__ wtab, int tid,
+                                              int nthreads) {
+    for (int idx = tid; idx < R * P0; idx += nthreads) {
+      const int m = idx / P0, k = idx % P0;
+      const double2 w = wtab[(2 * (H / (P0 * R)) * k * m) & (2 * H - 1)];
+      tw[idx] = cplx{w.x, w.y};
+    }
+    if constexpr (REM / R > 1) Stages<H, TPR, P0 * R, REM / R>::fill(tw + R * P0, wtab, tid, nthreads);
   }
 };
 
@@ -105,16 +115,18 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
   constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;   // threads per row
   constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;  // rows per CTA
   constexpr int NT = RPC * TPR;                      // active threads
-  constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1; // padded complex per row
+  constexpr int ROWLEN = (H + 1 + ((H + 1) >> 4) + 1) | 1;  // padded complex per row, odd
   extern __shared__ __align__(16) unsigned char zsm[];
-  cplx* wsm = reinterpret_cast<cplx*>(zsm);          // twiddle table e^{2 pi i j/M}, j < M
-  cplx* sm = wsm + M;                                // RPC padded rows
+  cplx* wsm = reinterpret_cast<cplx*>(zsm);          // pack twiddles e^{2 pi i k/M}, k <= H/2
+  cplx* tws = wsm + (H / 2 + 1);                     // per-stage twiddle tables (< 2H entries)
+  cplx* sm = tws + 2 * H;                            // RPC padded rows
 
   const int tid = threadIdx.x;
-  for (int j = tid; j < M; j += blockDim.x) {
+  for (int j = tid; j <= H / 2; j += blockDim.x) {
     const double2 w = wtab[j];
     wsm[j] = cplx{w.x, w.y};
   }
+  Stages<H, TPR, 1, H>::fill(tws, wtab, tid, blockDim.x);
   __syncthreads();
   const int64_t groups_per_plane = M / RPC;
   const int64_t ngroups = planes * groups_per_plane;
@@ -148,7 +160,7 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
     {
       const bool active = tid < NT;
       const int r = active ? tid / TPR : 0;
-      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, Kz, wsm);
+      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, Kz, tws);
     }
     // ---- write the rows: x[2n] = Re z[n], x[2n+1] = Im z[n]; z[n] is stored at padidx(n)
     for (int e = tid; e < RPC * H; e += blockDim.x) {
@@ -169,8 +181,8 @@ static int launch_zpass(const void* ycols, void* fields, int Kz, int64_t planes,
                         cudaStream_t st) {
   constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;
   constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;
-  constexpr int ROWLEN = H + 1 + ((H + 1) >> 4) + 1;
-  const size_t smem = ((size_t)RPC * ROWLEN + 2 * H) * sizeof(cplx);
+  constexpr int ROWLEN = (H + 1 + ((H + 1) >> 4) + 1) | 1;
+  const size_t smem = ((size_t)RPC * ROWLEN + 2 * H + H / 2 + 1) * sizeof(cplx);
   BSK_CUDA(cudaFuncSetAttribute(zpass_c2r_kernel<H, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   const int64_t ngroups = planes * (2 * H / RPC);

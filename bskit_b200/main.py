@@ -55,6 +55,12 @@ F32, F64 = 0, 1
 # --------------------------------------------------------------------------- #
 # engine management (lazy: importing this module needs neither torch nor a GPU)
 # --------------------------------------------------------------------------- #
+#: Test seam ONLY: tests/ may set this to a stand-in backend class to exercise the host logic
+#: (result dict, slicing, units, file formats, error paths) on a CPU-only box.  The product
+#: never sets it; with None every engine is the CUDA backend and raises without a GPU.
+_BACKEND_FOR_TESTS = None
+
+
 class _Session:
     """Engines for one (Nmesh, BoxSize) pair on this process's GPU."""
 
@@ -77,10 +83,11 @@ class _Session:
                                       self.grid_policy if policy is None else policy, self.world)
         key = (choice, precision)
         if key not in self._engines:
+            extra = {} if _BACKEND_FOR_TESTS is None else {"backend_cls": _BACKEND_FOR_TESTS}
             self._engines[key] = self.eng.Engine(choice, self.boxsize, precision,
                                                  device=self.device, group=self.group,
                                                  fft_precision=self.fft_precision,
-                                                 accum_precision=self.accum_precision)
+                                                 accum_precision=self.accum_precision, **extra)
         return self._engines[key]
 
     def compensation_tables(self, engine, comp):
