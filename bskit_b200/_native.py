@@ -21,7 +21,7 @@ EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
     "bsk_set_compensation", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
     "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_contract",
-    "bsk_launch_count",
+    "bsk_reduce_list", "bsk_launch_count",
 )
 
 
@@ -72,6 +72,7 @@ def lib():
     L.bsk_cplan_destroy.argtypes = [vp]
     L.bsk_cplan_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
+    L.bsk_reduce_list.argtypes = [C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

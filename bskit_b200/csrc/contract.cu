@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <unordered_map>
 
@@ -309,6 +310,67 @@ __global__ void fold_partials_kernel(const double* __restrict__ partial, int64_t
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Sparse triangle lists (equilateral, squeezed, isosceles: T ~ S, each triangle touches <= 3
+// fields): one streaming pass per triangle straight from HBM, no shared-memory tile.  Every
+// field value a triangle needs is read once for that triangle, fully coalesced 128-bit loads;
+// 16-cell float32 partial products, float64 from there on (warp shuffle + one RED per CTA).
+// HBM-bound: bytes = sum_t (distinct fields of t) * cells * sizeof(T).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+tri_stream_reduce_kernel(const T* const* __restrict__ rowptr, const int* __restrict__ tri,
+                         int64_t ncells, double* __restrict__ sums) {
+  using V = typename Vec<T>::type;
+  constexpr int W = Vec<T>::W;
+  const int t = blockIdx.y;
+  const V* __restrict__ pa = reinterpret_cast<const V*>(rowptr[tri[3 * t + 0]]);
+  const V* __restrict__ pb = reinterpret_cast<const V*>(rowptr[tri[3 * t + 1]]);
+  const V* __restrict__ pc = reinterpret_cast<const V*>(rowptr[tri[3 * t + 2]]);
+  const bool same_ab = pa == pb, same_bc = pb == pc, same_ac = pa == pc;
+  const int64_t nvec = ncells / W;
+  double dsum = 0.0;
+  constexpr int U = 4;  // independent 128-bit loads in flight per field per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+    V va[U], vb[U], vc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < nvec) {
+        va[u] = pa[v];
+        vb[u] = same_ab ? va[u] : pb[v];
+        vc[u] = same_bc ? vb[u] : (same_ac ? va[u] : pc[v]);
+      }
+    }
+    typename std::conditional<sizeof(T) == 4, float, double>::type part = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (v0 + u * stride < nvec) {
+        T a[W], b[W], c[W];
+        Vec<T>::unpack(va[u], a);
+        Vec<T>::unpack(vb[u], b);
+        Vec<T>::unpack(vc[u], c);
+#pragma unroll
+        for (int w = 0; w < W; ++w) part = fma(a[w] * b[w], c[w], part);
+      }
+    }
+    dsum += (double)part;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  __shared__ double wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += wsum[w];
+    atomicAdd(&sums[t], tot);
+  }
+}
+
 }  // namespace bsk
 
 struct bsk_cplan {
@@ -507,6 +569,46 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
   const int m = mode ? atoi(mode) : 1;
   if (m == 0) return contract_impl<float, float, 0>(cp, ncells, njobs, sums, st);
   return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
+}
+
+int bsk_reduce_list(const void* const* row_ptrs, int nrows, int precision, int64_t ncells, int ntri,
+                    const int32_t* rows, double* sums, void* cuda_stream) {
+  BSK_REQUIRE(row_ptrs && rows && sums && nrows > 0 && ntri > 0, "bsk_reduce_list: bad argument");
+  BSK_REQUIRE(ncells > 0 && ncells % 4 == 0, "bsk_reduce_list: ncells must be a positive multiple of 4");
+  BSK_REQUIRE(precision == BSK_F32 || precision == BSK_F64, "bsk_reduce_list: bad precision");
+  BSK_REQUIRE(ntri <= 65535, "bsk_reduce_list: at most 65535 triangles per call");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  for (int r = 0; r < nrows; ++r)
+    BSK_REQUIRE(row_ptrs[r] && ((uintptr_t)row_ptrs[r] % 16) == 0,
+                "bsk_reduce_list: row %d pointer is null or not 16-byte aligned", r);
+  for (int i = 0; i < 3 * ntri; ++i)
+    BSK_REQUIRE(rows[i] >= 0 && rows[i] < nrows, "bsk_reduce_list: row index %d outside [0,%d)", rows[i], nrows);
+  // small per-call tables, stream-ordered allocation (freed after the kernel)
+  const size_t pbytes = sizeof(void*) * (size_t)nrows, tbytes = sizeof(int) * 3 * (size_t)ntri;
+  unsigned char* d = nullptr;
+  BSK_CUDA(cudaMallocAsync((void**)&d, pbytes + tbytes, st));
+  BSK_CUDA(cudaMemcpyAsync(d, row_ptrs, pbytes, cudaMemcpyHostToDevice, st));
+  BSK_CUDA(cudaMemcpyAsync(d + pbytes, rows, tbytes, cudaMemcpyHostToDevice, st));
+  BSK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)ntri, st));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int W = precision == BSK_F32 ? 4 : 2;
+  const int64_t nvec = ncells / W;
+  int64_t gx = (sms * 24 + ntri - 1) / ntri;                       // ~24 CTAs per SM in total
+  const int64_t gx_max = (nvec + 256 * 4 - 1) / (256 * 4);
+  gx = std::max<int64_t>(1, std::min(gx, gx_max));
+  dim3 grid((unsigned)gx, (unsigned)ntri);
+  if (precision == BSK_F32)
+    tri_stream_reduce_kernel<float><<<grid, 256, 0, st>>>((const float* const*)d, (const int*)(d + pbytes), ncells, sums);
+  else
+    tri_stream_reduce_kernel<double><<<grid, 256, 0, st>>>((const double* const*)d, (const int*)(d + pbytes), ncells, sums);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  BSK_CUDA(cudaFreeAsync(d, st));
+  // the host tables may be reused by the caller as soon as we return
+  BSK_CUDA(cudaStreamSynchronize(st));
+  return BSK_OK;
 }
 
 }  // extern "C"

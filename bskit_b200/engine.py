@@ -278,6 +278,21 @@ class NativeBackend:
                       "bsk_contract")
         return sums
 
+    def reduce_list(self, fields, rows, ncells):
+        """Streaming per-triangle reduction for sparse lists; rows: (T,3) indices into fields.
+        Returns this rank's float64 sums [T] (CUDA tensor)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        nrows = len(fields)
+        ptrs = (C.c_void_p * nrows)(*[f.data_ptr() for f in fields])
+        sums = torch.empty(len(rows), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.bsk_reduce_list(ptrs, nrows, self.precision, ncells, len(rows),
+                                               rows.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               C.cast(sums.data_ptr(), C.POINTER(C.c_double)),
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                      "bsk_reduce_list")
+        return sums
+
     def cplan_info(self):
         """Schedule of the most recent contraction: blocks, split, rounds, threads."""
         cp = getattr(self, "_last_cplan", None)
@@ -300,6 +315,7 @@ class Engine:
         self.grid = grid
         self.max_rows = max_rows
         self.last_batches = 0
+        self.last_schedule = None
         self.boxsize = box3(boxsize)
         self.precision = precision
         self.group = group
@@ -427,7 +443,23 @@ class Engine:
         """
         if torch.is_tensor(fields):
             fields = [fields[r] for r in range(fields.shape[0])]
-        sums = self.backend.contract(fields, rows, int(fields[0].numel()), job_off)
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+        job_off = np.asarray(job_off, dtype=np.int64).reshape(-1, 3)
+        ncells = int(fields[0].numel())
+        # Sparse lists (each field feeds few triangles) stream straight from HBM, one pass per
+        # triangle; dense lists go through the shared-memory tile kernel.  Cost model: bytes.
+        self.last_schedule = "tile"
+        ntot = len(rows) * len(job_off)
+        if hasattr(self.backend, "reduce_list") and ntot <= min(65535, 2 * len(fields)):
+            allrows = (rows[None, :, :] + job_off[:, None, :]).reshape(-1, 3)
+            srt = np.sort(allrows, axis=1)
+            per_tri = 1 + (srt[:, 1] != srt[:, 0]) + (srt[:, 2] != srt[:, 1])
+            if per_tri.sum() <= 2 * len(np.unique(allrows)):
+                self.last_schedule = "stream"
+        if self.last_schedule == "stream":
+            sums = self.backend.reduce_list(fields, allrows, ncells).reshape(len(job_off), len(rows))
+        else:
+            sums = self.backend.contract(fields, rows, ncells, job_off)
         _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)

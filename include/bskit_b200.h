@@ -163,6 +163,15 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
                  int64_t ncells, int njobs, const int32_t* job_off, double* sums,
                  void* cuda_stream);
 
+/* Sparse triangle lists (equilateral / squeezed / isosceles, T ~ S: every triangle touches
+ * <= 3 fields): one coalesced streaming pass per triangle straight from HBM,
+ *     sums[t] = sum_x F[rows[t][0]](x) * F[rows[t][1]](x) * F[rows[t][2]](x)
+ * (the same np.sum of main.py:1875 / 2027-2055, for lists where the 4x4x4-block schedule of
+ * bsk_contract would waste work).  row_ptrs, rows: HOST arrays; sums: device float64[ntri].
+ * Returns after the work is enqueued and the host tables have been consumed. */
+int bsk_reduce_list(const void* const* row_ptrs, int nrows, int precision, int64_t ncells, int ntri,
+                    const int32_t* rows, double* sums, void* cuda_stream);
+
 /* number of kernels this library has launched since load (bench bookkeeping) */
 int64_t bsk_launch_count(void);
 

@@ -435,3 +435,25 @@ def test_c3_512_isosceles_and_squeezed_cross(bk, syn):
                                         delta_k=[dk_a, dk_b])
         rms = np.sqrt(np.mean(got ** 2))
         assert np.all(np.abs(got[pick] - want) <= RTOL_B * np.abs(want) + 1e-6 * rms), (got[pick], want)
+
+
+def test_integration_md_ctypes_stub_runs(bk, syn):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer would paste into
+    bskit/main.py) is executed verbatim against the built library and checked with the oracle."""
+    import re
+    from conftest import ROOT
+    from bskit_b200 import _native
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if "_gpu_fast_bispectrum" in b][0]
+    stub = stub.replace('C.CDLL("libbskit_b200.so")', f'C.CDLL({_native.LIB_PATH!r})')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    n, nb = 64, 10
+    kmin, kmax, dk = syn.bench_bins(nb)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    mesh = syn.lognormal_mesh(n, seed=1)
+    got = ns["_gpu_fast_bispectrum"](mesh, syn.BOX, edges, idx)
+    want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
+    assert_b_close(got, want)
