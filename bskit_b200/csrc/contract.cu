@@ -181,8 +181,8 @@ __device__ __forceinline__ void accumulate_slice(typename AccOf<TC, PACKED>::typ
 //    the kernel is HBM-bound): a thread keeps ONE unit's accumulators in registers across tiles
 //    and reduces them every `flush_every` tiles, so the float64 reductions do not outnumber
 //    the loads.
-template <typename T, typename TC, int PACKED, bool PERSIST>
-__global__ void __launch_bounds__(kThreads, 1)
+template <typename T, typename TC, int PACKED, bool PERSIST, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
                      const int4* __restrict__ blocks, int nblocks, int split, int njobs,
                      const int* __restrict__ joboff, double* __restrict__ partial,
@@ -265,7 +265,7 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
         }
       }
     } else {
-      for (int u = tid; u < units; u += kThreads) {
+      for (int u = tid; u < units; u += THREADS) {
         const int b = u % nblocks;
         const int g = u / nblocks;
         const int q0 = (int)(((int64_t)nq * g) / split);
@@ -373,6 +373,23 @@ tri_stream_reduce_kernel(const T* const* __restrict__ rowptr, const int* __restr
 
 }  // namespace bsk
 
+// split each block's tile over `split` threads so that a round fills the CTA
+static int choose_split(int nblocks, int threads) {
+  int best = 1;
+  double best_eff = 0.0;
+  const int gmax = nblocks * 8 <= threads ? threads / nblocks : 8;
+  for (int g = 1; g <= gmax; ++g) {
+    const int units = nblocks * g;
+    const int rounds = (units + threads - 1) / threads;
+    const double eff = (double)units / ((double)rounds * threads);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = g;
+    }
+  }
+  return best;
+}
+
 struct bsk_cplan {
   int ntri = 0, nrows = 0, nblocks = 0, split = 1, rounds = 1, max_jobs = 1;
   int sm_count = 148;
@@ -391,8 +408,9 @@ struct bsk_cplan {
 
 using namespace bsk;
 
-template <typename T, typename TC, int PACKED>
+template <typename T, typename TC, int PACKED, int THREADS = kThreads>
 static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums, cudaStream_t st) {
+  const int split = choose_split(cp->nblocks, THREADS);
   // tile size: double-buffered [nrows][tile_cells] must fit in shared memory
   const size_t budget = std::min<size_t>(cp->smem_limit, 227 * 1024) - 1024;
   int tile = (int)(budget / (2 * (size_t)cp->nrows * sizeof(T)));
@@ -404,16 +422,16 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   const int ncta = (int)std::min<int64_t>(ntiles, cp->ncta_alloc);
   const size_t smem = 128 + 2 * (size_t)cp->nrows * tile * sizeof(T);
   const int64_t stride = (int64_t)njobs * 64 * cp->nblocks;
-  const bool persist = (cp->nblocks * cp->split <= kThreads) && njobs == 1;
+  const bool persist = (cp->nblocks * split <= THREADS) && njobs == 1;
   // the sparse-list schedule is HBM-bound: it uses the scalar (spill-free) inner loop
-  auto kern = persist ? tile_contract_kernel<T, TC, 0, true>
-                      : tile_contract_kernel<T, TC, PACKED, false>;
+  auto kern = persist ? tile_contract_kernel<T, TC, 0, true, THREADS>
+                      : tile_contract_kernel<T, TC, PACKED, false, THREADS>;
   BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
   // sparse-list schedule: reduce into float64 after ~1024 cells per thread
-  const int flush_every = std::max(1, (1024 * cp->split) / tile);
-  kern<<<ncta, kThreads, smem, st>>>(
-      (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, cp->split,
+  const int flush_every = std::max(1, (1024 * split) / tile);
+  kern<<<ncta, THREADS, smem, st>>>(
+      (const T* const*)cp->d_rowptr, cp->nrows, ncells, tile, cp->d_blocks, cp->nblocks, split,
       njobs, cp->d_joboff, cp->d_partial, stride, flush_every);
   count_launch();
   BSK_CUDA(cudaGetLastError());
@@ -466,19 +484,7 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
     const uint64_t key = ((uint64_t)(r1 >> 2) << 40) | ((uint64_t)(r2 >> 2) << 20) | (uint64_t)(r3 >> 2);
     slot[t] = slot[t] * cp->nblocks + index[key];
   }
-  // split each block's tile over `split` threads so that a round fills the CTA
-  int best = 1;
-  double best_eff = 0.0;
-  const int gmax = cp->nblocks * 8 <= kThreads ? kThreads / cp->nblocks : 8;
-  for (int g = 1; g <= gmax; ++g) {
-    const int units = cp->nblocks * g;
-    const int rounds = (units + kThreads - 1) / kThreads;
-    const double eff = (double)units / ((double)rounds * kThreads);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
-      best = g;
-    }
-  }
+  const int best = choose_split(cp->nblocks, kThreads);
   cp->split = best;
   cp->rounds = (cp->nblocks * best + kThreads - 1) / kThreads;
 
