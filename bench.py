@@ -358,15 +358,19 @@ def main():
     useful_flops = 2.0 * cells * ntri + cells * 820.0 * (len(edges) == 40)
     issued = full["cplan"]["nblocks"] * 80.0 * 2.0 * cells if full["cplan"] else None
     clk = (full["clocks"] or {}).get("sm_mhz") or 1900.0
-    fp32_peak = 148 * 128 * 2 * clk * 1e6
+    fp32_peak = 72.5e12 * clk / 1965.0        # measured by scripts/dev/ffma_probe.cu at 1965 MHz
     roofline = {"kernel": "tile_contract_kernel<float,%s>" % ("float" if accum == nat.F32 else "double"),
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+                # kernel at this exact configuration (profiles/r1_tile_contract_packed_ncu_raw.csv)
+                "traffic": 21.513e9 if (nmesh == 512 and len(edges) == 40 and world == 1) else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_contract * 1e3,
                 "note": "the kernel is FP32-FMA-pipe bound, not HBM bound: see fp32_pipe",
                 "fp32_pipe": {"issued_flops_per_launch": issued, "useful_flops_per_launch": useful_flops,
                               "issued_tflops": (issued / t_contract / 1e12) if issued else None,
-                              "peak_tflops_at_sampled_clock": fp32_peak / 1e12,
+                              "peak_tflops_measured_ffma_probe": fp32_peak / 1e12,
                               "frac_issued": (issued / t_contract / fp32_peak) if issued else None}}
     shells_bytes = float(len(edges)) * full["ncells"] * (8 * (nmesh // 2 + 1) / nmesh + 4)
     stage_roofs = {"shells": {"algorithmic_bytes": shells_bytes,
