@@ -47,6 +47,7 @@ __all__ = [
     "number_field", "k_field", "pk_FFT", "compute_Nbin", "compute_k_means_on_grid",
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
     "combine_gridinfo_and_unnormalized", "clear_cache",
+    "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm",
 ]
 
 F32, F64 = 0, 1
@@ -366,6 +367,38 @@ def pk_FFT(mesh, kmin, kmax):
         return out[2] * meas.volume() / nbin, nbin, out[1] / nbin
     finally:
         meas.release()
+
+
+def subbox_multiindex_to_index(multiindex, nsub_per_side):
+    """(a,b,c) -> a*N^2 + b*N + c (ref. main.py:30-51)."""
+    assert len(multiindex) == 3
+    return int(multiindex[0] * nsub_per_side ** 2 + multiindex[1] * nsub_per_side + multiindex[2])
+
+
+def subbox_index_to_multiindex(i, nsub_per_side):
+    """Inverse of :func:`subbox_multiindex_to_index` (ref. main.py:54-81); float array like the
+    reference's."""
+    m = np.zeros(3)
+    q, r = divmod(i, nsub_per_side ** 2)
+    m[0] = q
+    m[1], m[2] = divmod(r, nsub_per_side)
+    return m
+
+
+def field_subbox_pm(box_multiindex, nsub_per_side, source):
+    """Cut the (Nmesh/nsub)^3 sub-cube with origin ``box_multiindex * Nmesh/nsub`` out of a mesh
+    (ref. main.py:84-147, which does it with pmesh decompose/readout/paint and the nearest-grid-
+    point resampler, i.e. an exact copy of the cells).  Returns an :class:`ArrayMesh` with
+    ``BoxSize/nsub``; numpy and torch (host or device) arrays are sliced without a host round trip."""
+    mesh = source if isinstance(source, ArrayMesh) else cast_source(source)
+    n = int(mesh.attrs["Nmesh"][0])
+    if n % int(nsub_per_side):
+        raise ValueError("Nmesh must be divisible by nsub_per_side")
+    ns = n // int(nsub_per_side)
+    i0 = [int(round(float(b))) * ns for b in box_multiindex]
+    sub = mesh.array[i0[0]:i0[0] + ns, i0[1]:i0[1] + ns, i0[2]:i0[2] + ns]
+    sub = np.ascontiguousarray(sub) if isinstance(sub, np.ndarray) else sub.contiguous()
+    return ArrayMesh(sub, mesh.attrs["BoxSize"] / float(nsub_per_side), compensation=mesh.compensation)
 
 
 def combine_gridinfo_and_unnormalized(bin_info, b_vals, k_max=np.inf, tol=0.01):

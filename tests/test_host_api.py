@@ -117,3 +117,30 @@ def test_empty_bins_give_zero_count_and_nan_kmean():
     r = fb.measure_gridinfo_faster()
     assert r["N_tri"][0] == 0 and np.isnan(r["k_mean"][0]).all()
     assert r["N_tri"][-1] > 0 and np.isfinite(r["k_mean"][-1]).all()
+
+
+def test_subbox_helpers_and_subbox_gridinfo_golden(tmp_path):
+    """Sub-box path: index helpers (main.py:30-81), exact sub-cube extraction, and
+    the sub-box golden: bins stay in full-box units, so in the L=500 sub-box every triangle
+    touching bin 0 is empty (N_tri = 0, k_mean = nan) and the others match the golden digits."""
+    assert bk.subbox_multiindex_to_index((1, 0, 1), 2) == 5
+    assert np.array_equal(bk.subbox_index_to_multiindex(5, 2), [1, 0, 1])
+    for i in range(8):
+        assert bk.subbox_multiindex_to_index(bk.subbox_index_to_multiindex(i, 2), 2) == i
+    full = np.arange(16 ** 3, dtype=np.float64).reshape(16, 16, 16)
+    sub = bk.field_subbox_pm(np.array([1, 0, 1]), 2, bk.ArrayMesh(full, 1000.0))
+    assert np.array_equal(sub.array, full[8:16, 0:8, 8:16])
+    assert np.array_equal(sub.attrs["BoxSize"], [500.0] * 3) and np.array_equal(sub.attrs["Nmesh"], [8] * 3)
+    with pytest.raises(ValueError):
+        bk.field_subbox_pm((0, 0, 0), 3, bk.ArrayMesh(full, 1000.0))
+    # sub-box of a 96^3 mesh -> 48^3, L = 500: first block of the reference's sub-box golden
+    g = np.loadtxt(os.path.join(REF_OUT, "Lbox1000_512_kf_3kf_3lowkbins_subbox0.dat"))[:59]
+    src = bk.field_subbox_pm((0, 0, 0), 2, bk.ArrayMesh(np.zeros((96, 96, 96)), 1000.0))
+    fb = bk.FFTBispectrum(src, for_grid_info_only=True, device=torch.device("cpu"), **BINS)
+    r = fb.measure_gridinfo_faster(0, 200)
+    for t in range(59):
+        if abs(g[t, 10]) < 0.5 or not np.isfinite(g[t, 1:4]).all():
+            assert r["N_tri"][t] == 0 and np.isnan(r["k_mean"][t]).all()
+        else:
+            assert fmt_e(r["N_tri"][t]) == fmt_e(g[t, 10])
+            assert [fmt_e(v) for v in r["k_mean"][t]] == [fmt_e(v) for v in g[t, 1:4]]
