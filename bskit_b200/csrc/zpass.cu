@@ -40,15 +40,21 @@ __global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __r
   }
 }
 
+constexpr int kZThreads = 128;  // small CTAs: 4-5 resident per SM, cheap barriers
+
 __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }  // 1 pad per 16 complex
 
 // One Stockham stage of radix R on the rows of this CTA.  TPR threads cooperate on a row.
 // In the first stage (p == 1) only packed entries with index < Kz or > H-Kz can be non-zero
 // (the rest were never written): they are taken as zero without touching shared memory.
-template <int R, int H, int TPR>
+// The LAST stage writes its outputs straight to global memory from registers (x[2n] = Re z[n],
+// x[2n+1] = Im z[n]; lanes hold consecutive n, so each warp store covers whole 128-byte lines)
+// instead of going back through shared memory.
+template <int R, int H, int TPR, bool LAST, typename TS>
 __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, int p, bool active,
                                                int Kz,
-                                               const cplx* __restrict__ tw /* smem [R][p]: e^{2 pi i k m/(pR)} */) {
+                                               const cplx* __restrict__ tw /* smem [R][p]: e^{2 pi i k m/(pR)} */,
+                                               TS* __restrict__ out_row) {
   constexpr int T = H / R;          // butterflies per row in this stage
   constexpr int PER = T / TPR;      // butterflies per thread (TPR = H/16, so PER = 16/R)
   cplx v[PER][R];
@@ -77,22 +83,35 @@ __device__ __forceinline__ void stockham_stage(cplx* __restrict__ row, int lt, i
     const int i = lt + b * TPR;
     const int k = i & (p - 1);
     const int j = (i - k) * R + k;
+    if constexpr (LAST) {
 #pragma unroll
-    for (int m = 0; m < R; ++m) row[padidx(j + m * p)] = v[b][zfft::bitrev<R>(m)];
+      for (int m = 0; m < R; ++m) {
+        const cplx z = v[b][zfft::bitrev<R>(m)];
+        TS* dst = out_row + 2 * (j + m * p);
+        if (sizeof(TS) == 4)
+          *reinterpret_cast<float2*>(dst) = make_float2((float)z.x, (float)z.y);
+        else
+          *reinterpret_cast<double2*>(dst) = make_double2(z.x, z.y);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) row[padidx(j + m * p)] = v[b][zfft::bitrev<R>(m)];
+    }
   }
   }
-  __syncthreads();
+  if constexpr (!LAST) __syncthreads();
 }
 
 template <int H, int TPR, int P0, int REM>
 struct Stages {
   static constexpr int R = (REM % 16 == 0) ? 16 : (REM % 8 == 0) ? 8 : (REM % 4 == 0) ? 4 : 2;
   // per-stage twiddle tables are stored back to back: [R][P0] entries each
+  template <typename TS>
   static __device__ __forceinline__ void run(cplx* row, int lt, bool active, int Kz,
-                                             const cplx* tw) {
-    stockham_stage<R, H, TPR>(row, lt, P0, active, Kz, tw);
+                                             const cplx* tw, TS* out_row) {
+    stockham_stage<R, H, TPR, (REM / R == 1), TS>(row, lt, P0, active, Kz, tw, out_row);
     if constexpr (REM / R > 1)
-      Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, Kz, tw + R * P0);
+      Stages<H, TPR, P0 * R, REM / R>::run(row, lt, active, Kz, tw + R * P0, out_row);
   }
   static __device__ __forceinline__ void fill(cplx* tw, const double2* __restrict__ wtab, int tid,
                                               int nthreads) {
@@ -107,13 +126,13 @@ struct Stages {
 
 // M = 2H.  Rows are (plane, y); a CTA handles RPC consecutive y of one plane.
 template <int H, typename TS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kZThreads)
 zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
                  TS* __restrict__ fields,            // [planes][M][M]
                  int Kz, int64_t planes, const double2* __restrict__ wtab) {
   constexpr int M = 2 * H;
   constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;   // threads per row
-  constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;  // rows per CTA
+  constexpr int RPC = kZThreads / TPR > 32 ? 32 : kZThreads / TPR;  // rows per CTA
   constexpr int NT = RPC * TPR;                      // active threads
   constexpr int ROWLEN = (H + 1 + ((H + 1) >> 4) + 1) | 1;  // padded complex per row, odd
   extern __shared__ __align__(16) unsigned char zsm[];
@@ -156,23 +175,15 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
       }
     }
     __syncthreads();
-    // ---- Stockham stages: every thread runs the barriers, threads without a row do no work
+    // ---- Stockham stages: every thread runs the barriers, threads without a row do no work;
+    //      the last stage stores the finished rows to global memory
     {
       const bool active = tid < NT;
       const int r = active ? tid / TPR : 0;
-      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, Kz, tws);
+      TS* out_row = fields + ((int64_t)plane * M + y0 + r) * M;
+      Stages<H, TPR, 1, H>::run(sm + r * ROWLEN, tid % TPR, active, Kz, tws, out_row);
     }
-    // ---- write the rows: x[2n] = Re z[n], x[2n+1] = Im z[n]; z[n] is stored at padidx(n)
-    for (int e = tid; e < RPC * H; e += blockDim.x) {
-      const int r = e / H, n = e % H;
-      const cplx z = sm[r * ROWLEN + padidx(n)];
-      TS* dst = fields + ((int64_t)plane * M + y0 + r) * M + 2 * n;
-      if (sizeof(TS) == 4)
-        *reinterpret_cast<float2*>(dst) = make_float2((float)z.x, (float)z.y);
-      else
-        *reinterpret_cast<double2*>(dst) = make_double2(z.x, z.y);
-    }
-    __syncthreads();
+    // the last stage synchronised after reading shared memory, so the next group may load
   }
 }
 
@@ -180,14 +191,14 @@ template <int H, typename TS>
 static int launch_zpass(const void* ycols, void* fields, int Kz, int64_t planes, const double2* wtab,
                         cudaStream_t st) {
   constexpr int TPR = (H / 16) > 0 ? (H / 16) : 1;
-  constexpr int RPC = 256 / TPR > 32 ? 32 : 256 / TPR;
+  constexpr int RPC = kZThreads / TPR > 32 ? 32 : kZThreads / TPR;
   constexpr int ROWLEN = (H + 1 + ((H + 1) >> 4) + 1) | 1;
   const size_t smem = ((size_t)RPC * ROWLEN + 2 * H + H / 2 + 1) * sizeof(cplx);
   BSK_CUDA(cudaFuncSetAttribute(zpass_c2r_kernel<H, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   const int64_t ngroups = planes * (2 * H / RPC);
-  const int grid = (int)(ngroups < 148 * 8 ? ngroups : 148 * 8);
-  zpass_c2r_kernel<H, TS><<<grid, 256, smem, st>>>((const double2*)ycols, (TS*)fields, Kz, planes, wtab);
+  const int grid = (int)(ngroups < 148 * 16 ? ngroups : 148 * 16);
+  zpass_c2r_kernel<H, TS><<<grid, kZThreads, smem, st>>>((const double2*)ycols, (TS*)fields, Kz, planes, wtab);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   return BSK_OK;
