@@ -105,31 +105,52 @@ __device__ __forceinline__ double acc_value(float v) { return (double)v; }
 __device__ __forceinline__ double acc_value(double v) { return v; }
 __device__ __forceinline__ double acc_value(float2 v) { return (double)v.x + (double)v.y; }
 
+// 128-bit shared-memory loads from 32-bit shared addresses: the address arithmetic stays on the
+// integer ALU (IADD3) instead of 64-bit IMADs, which share the FMA pipe with the real work.
+__device__ __forceinline__ float4 lds_vec(uint32_t addr, float4*) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_vec(uint32_t addr, double2*) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 // Add the n vectors [0,n) of three groups of four rows into the 4x4x4 accumulators.
 // PACKED (float only): two cells per instruction with Blackwell's packed FP32 math (FMUL2 /
 // FFMA2, fma.rn.f32x2): the (x,y) and (z,w) halves of each 128-bit shared-memory load are
 // already aligned register pairs, so the loop issues half as many instructions for the same
 // FMA-pipe work.  The cell order is rotated per lane so that lanes reading different rows hit
 // different banks.
-template <typename T, typename TC, int PACKED>
+template <typename T, typename TC, int PACKED, int TILE = 0>
 __device__ __forceinline__ void accumulate_slice(typename AccOf<TC, PACKED>::type (&acc)[64],
                                                  const typename Vec<T>::type* __restrict__ pa,
                                                  const typename Vec<T>::type* __restrict__ pb,
                                                  const typename Vec<T>::type* __restrict__ pc, int n,
                                                  int rot, int rowstride_v) {
   constexpr int W = Vec<T>::W;
+  using V = typename Vec<T>::type;
+  const uint32_t sa = smem_u32(pa), sb = smem_u32(pb), sc = smem_u32(pc);
+  // with a compile-time tile length the row offsets fold into the LDS immediates
+  const uint32_t rs1 = TILE ? (uint32_t)(TILE * sizeof(T)) : (uint32_t)rowstride_v * 16u;
+  const uint32_t rs2 = 2u * rs1, rs3 = 3u * rs1;
+  const uint32_t lim = (uint32_t)n * 16u;
+  uint32_t off = (uint32_t)rot * 16u;
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
-    int q = i + rot;
-    if (q >= n) q -= n;
+    const uint32_t oa = sa + off, ob = sb + off, oc = sc + off;
+    off += 16u;
+    if (off == lim) off = 0u;
     if constexpr (PACKED == 1) {
       float4 va[4], vb[4], vc[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        va[r] = pa[(size_t)r * rowstride_v + q];
-        vb[r] = pb[(size_t)r * rowstride_v + q];
-        vc[r] = pc[(size_t)r * rowstride_v + q];
-      }
+      va[0] = lds_vec(oa, (V*)nullptr); va[1] = lds_vec(oa + rs1, (V*)nullptr);
+      va[2] = lds_vec(oa + rs2, (V*)nullptr); va[3] = lds_vec(oa + rs3, (V*)nullptr);
+      vb[0] = lds_vec(ob, (V*)nullptr); vb[1] = lds_vec(ob + rs1, (V*)nullptr);
+      vb[2] = lds_vec(ob + rs2, (V*)nullptr); vb[3] = lds_vec(ob + rs3, (V*)nullptr);
+      vc[0] = lds_vec(oc, (V*)nullptr); vc[1] = lds_vec(oc + rs1, (V*)nullptr);
+      vc[2] = lds_vec(oc + rs2, (V*)nullptr); vc[3] = lds_vec(oc + rs3, (V*)nullptr);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float2 a2[4], b2[4], c2[4];
@@ -153,9 +174,10 @@ __device__ __forceinline__ void accumulate_slice(typename AccOf<TC, PACKED>::typ
       TC a[4][W], bb[4][W], c[4][W];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        Vec<T>::unpack(pa[(size_t)r * rowstride_v + q], a[r]);
-        Vec<T>::unpack(pb[(size_t)r * rowstride_v + q], bb[r]);
-        Vec<T>::unpack(pc[(size_t)r * rowstride_v + q], c[r]);
+        const uint32_t ro = (uint32_t)r * rs1;
+        Vec<T>::unpack(lds_vec(oa + ro, (V*)nullptr), a[r]);
+        Vec<T>::unpack(lds_vec(ob + ro, (V*)nullptr), bb[r]);
+        Vec<T>::unpack(lds_vec(oc + ro, (V*)nullptr), c[r]);
       }
 #pragma unroll
       for (int w = 0; w < W; ++w)
@@ -181,7 +203,7 @@ __device__ __forceinline__ void accumulate_slice(typename AccOf<TC, PACKED>::typ
 //    the kernel is HBM-bound): a thread keeps ONE unit's accumulators in registers across tiles
 //    and reduces them every `flush_every` tiles, so the float64 reductions do not outnumber
 //    the loads.
-template <typename T, typename TC, int PACKED, bool PERSIST, int THREADS>
+template <typename T, typename TC, int PACKED, bool PERSIST, int THREADS, int TILE = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t ncells, int tile_cells,
                      const int4* __restrict__ blocks, int nblocks, int split, int njobs,
@@ -276,7 +298,7 @@ tile_contract_kernel(const T* const* __restrict__ rowptr, int nrows, int64_t nce
         const int rot = lane % n;
         for (int job = 0; job < njobs; ++job) {
           acc_zero(acc);
-          accumulate_slice<T, TC, PACKED>(
+          accumulate_slice<T, TC, PACKED, TILE>(
               acc, tv + (size_t)(blk.x + joboff[3 * job + 0]) * rowstride_v + q0,
               tv + (size_t)(blk.y + joboff[3 * job + 1]) * rowstride_v + q0,
               tv + (size_t)(blk.z + joboff[3 * job + 2]) * rowstride_v + q0, n, rot, rowstride_v);
@@ -426,6 +448,10 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   // the sparse-list schedule is HBM-bound: it uses the scalar (spill-free) inner loop
   auto kern = persist ? tile_contract_kernel<T, TC, 0, true, THREADS>
                       : tile_contract_kernel<T, TC, PACKED, false, THREADS>;
+  if constexpr (PACKED == 1) {   // common tile lengths get immediate row offsets (S <= 40, S <= 80)
+    if (!persist && tile == 640) kern = tile_contract_kernel<T, TC, PACKED, false, THREADS, 640>;
+    if (!persist && tile == 320) kern = tile_contract_kernel<T, TC, PACKED, false, THREADS, 320>;
+  }
   BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BSK_CUDA(cudaMemsetAsync(cp->d_partial, 0, sizeof(double) * (size_t)ncta * stride, st));
   // sparse-list schedule: reduce into float64 after ~1024 cells per thread
