@@ -373,10 +373,29 @@ class Engine:
                 t = t.to(self.device)
         return t.contiguous()
 
-    def forward(self, mesh, compensation=None):
-        """delta_k cube of `mesh` (1/N^3-normalised, compensated, cropped)."""
+    def upload_async(self, mesh):
+        """Start the host-to-device copy of this rank's slab on a side stream and return
+        (device slab, event).  The copy engine then runs beside whatever the compute stream is
+        doing (e.g. the mesh-independent normalisation); `forward` waits for the event."""
+        if self.device.type != "cuda":
+            return self.local_slab(mesh), None
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            slab = self.local_slab(mesh)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return slab, ev
+
+    def forward(self, mesh, compensation=None, ready=None):
+        """delta_k cube of `mesh` (1/N^3-normalised, compensated, cropped).  `ready`: event of
+        an `upload_async` whose slab is passed as `mesh`."""
         self.backend.set_compensation(compensation)
+        if ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(ready)
         slab = self.local_slab(mesh)
+        if ready is not None:
+            slab.record_stream(torch.cuda.current_stream(self.device))
         planes = self.backend.forward_local(slab)
         if self.world > 1:
             n = self.grid.nmesh

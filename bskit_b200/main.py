@@ -203,6 +203,7 @@ class _Measurer:
     def release(self):
         """Drop this object's spectra; the shared session stays cached for the next object."""
         self._cubes = {}
+        self._uploads = None
         if self._session_key is not None:
             _release_session(self._session_key)
             self._session_key = None
@@ -210,13 +211,25 @@ class _Measurer:
     def volume(self):
         return float(self.boxsize.prod())
 
+    def prefetch(self, engine):
+        """Start uploading the mesh(es) (side stream); the forward transform itself is enqueued
+        by `cubes` when the first data measurement needs it."""
+        if getattr(self, "_uploads", None) is None:
+            self._uploads = (id(engine), [engine.upload_async(m.array) for m in self.meshes])
+
     def cubes(self, engine):
         key = id(engine)
         if key not in self._cubes:
             out = []
-            for m in self.meshes:
+            ups = getattr(self, "_uploads", None)
+            for i, m in enumerate(self.meshes):
                 comp = self.session.compensation_tables(engine, m.compensation)
-                out.append(engine.forward(m.array, comp))
+                if ups is not None and ups[0] == key:
+                    slab, ev = ups[1][i]
+                    out.append(engine.forward(slab, comp, ready=ev))
+                else:
+                    out.append(engine.forward(m.array, comp))
+            self._uploads = None
             self._cubes = {key: out}      # keep one set: a new crop radius replaces the old
         return self._cubes[key]
 
@@ -532,13 +545,15 @@ class FFTBispectrum:
         return self._measurer
 
     def _paint_meshes(self):
-        """Forward-transform the mesh(es) once (ref. main.py:1608-1621).  The spectrum is
-        cropped to the modes the binning can reach, so this needs the bin edges."""
+        """Start the one-off forward transform of the mesh(es) (ref. main.py:1608-1621): the
+        upload to the GPU begins here on a side stream; the transform (cropped to the modes the
+        binning can reach) is enqueued when the first data measurement asks for the spectrum, so
+        a `measure_gridinfo_faster` issued in between overlaps with the copy."""
         meas = self._meas()
         unit = max(1.0, float(self.attrs["pos_units_mpcoverh"]))
         kmax = float(np.max(np.asarray(self.k_edges)[:, 1::2])) * unit if len(self.k_edges) else None
         if kmax is not None:
-            meas.cubes(meas.session.engine(kmax, meas.precision))
+            meas.prefetch(meas.session.engine(kmax, meas.precision))
         self.attrs["painted"] = True
 
     def _rank0(self):
