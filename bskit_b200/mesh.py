@@ -40,12 +40,13 @@ class ArrayMesh:
 
     def __init__(self, array, BoxSize, compensation=None):
         shape = tuple(array.shape)
-        if len(shape) != 3 or not (shape[0] == shape[1] == shape[2]):
-            raise ValueError(f"mesh must be a cubic 3-D array, got shape {shape}")
+        # (N,N,N), or this rank's x-slab (N/world, N, N) of a mesh sharded over ranks
+        if len(shape) != 3 or shape[1] != shape[2] or shape[0] > shape[1] or shape[1] % shape[0]:
+            raise ValueError(f"mesh must be a cubic 3-D array (or an x-slab of one), got shape {shape}")
         self.array = array
         box = np.atleast_1d(np.asarray(BoxSize, dtype=np.float64)).ravel()
         self.attrs = {"BoxSize": np.ones(3) * box if box.size == 1 else box.copy(),
-                      "Nmesh": np.array(shape, dtype=np.int64)}
+                      "Nmesh": np.array([shape[1]] * 3, dtype=np.int64)}
         self.compensation = compensation
 
     def apply(self, func, kind="circular", mode="complex"):
