@@ -457,3 +457,74 @@ def test_integration_md_ctypes_stub_runs(bk, syn):
     got = ns["_gpu_fast_bispectrum"](mesh, syn.BOX, edges, idx)
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx, workers=4)
     assert_b_close(got, want)
+
+
+def test_schedule_choice_and_direct_c_calls(bk, syn):
+    """Sparse lists stream per triangle (bsk_reduce_list), dense lists use the tile kernel;
+    both agree with a float64 torch reduction.  Duplicate triangles are rejected by the C ABI."""
+    import ctypes as C
+    import torch
+    from bskit_b200 import engine as eng, _native as nat
+    dev = torch.device("cuda", 0)
+    n = 32
+    g = eng.choose_grid(n, syn.BOX, 8.5 * syn.KF, "full")
+    for prec, dt in ((nat.F32, torch.float32), (nat.F64, torch.float64)):
+        e = eng.Engine(g, syn.BOX, prec, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(5)
+        table = torch.randn((8, e.ncells), dtype=dt, device=dev, generator=gen)
+        t64 = table.double()
+        eq = np.array([[i, i, i] for i in range(8)])
+        got = e.contract(table, eq)[0]
+        assert e.last_schedule == "stream"
+        want = np.array([(t64[i] ** 3).sum().item() for i in range(8)])
+        np.testing.assert_allclose(got, want, rtol=2e-6 if prec == nat.F32 else 1e-12,
+                                   atol=1e-6 * np.abs(want).max() if prec == nat.F32 else 0)
+        dense = np.array([[a, b, c] for a in range(8) for b in range(a + 1) for c in range(b + 1)])
+        got = e.contract(table, dense)[0]
+        assert e.last_schedule == "tile"
+        want = np.array([(t64[a] * t64[b] * t64[c]).sum().item() for a, b, c in dense])
+        np.testing.assert_allclose(got, want, rtol=2e-5 if prec == nat.F32 else 1e-11,
+                                   atol=2e-6 * np.abs(want).max() if prec == nat.F32 else 0)
+        e.close()
+    lib = nat.lib()
+    rows = np.array([[0, 0, 0], [0, 0, 0]], dtype=np.int32)
+    cp = C.c_void_p()
+    rc = lib.bsk_cplan_create(C.byref(cp), 2, rows.ctypes.data_as(C.POINTER(C.c_int32)), 4, 1)
+    assert rc == -1
+    assert b"duplicate" in lib.bsk_last_error()
+
+
+def test_two_gpu_run_matches_single_gpu(bk, syn, tmp_path):
+    """x-slab sharding over two real GPUs (NCCL): same numbers as one GPU.  Skipped on a
+    single-GPU box; the host logic is also covered under gloo in tests/test_multirank_gloo.py."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "two_gpu.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bskit_b200 as bk\nfrom bskit_b200 import synthetic as syn\n"
+        "lr = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(lr)\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', lr))\n"
+        "kmin, kmax, dk = syn.bench_bins(10)\n"
+        "mesh = syn.lognormal_mesh(64, seed=1)\n"
+        "fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid='full', device=torch.device('cuda', lr))\n"
+        "b = fb.measure_bispectrum_faster(0, 10**9)['B']; g = fb.measure_gridinfo_faster(0, 10**9)\n"
+        f"if dist.get_rank() == 0: np.savez({str(tmp_path / 'out.npz')!r}, B=b, N=g['N_tri'], K=g['k_mean'])\n"
+        "dist.destroy_process_group()\n")
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)])
+    out = np.load(tmp_path / "out.npz")
+    kmin, kmax, dk = syn.bench_bins(10)
+    mesh = syn.lognormal_mesh(64, seed=1)
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="full")
+    b1 = fb.measure_bispectrum_faster(0, 10 ** 9)["B"]
+    g1 = fb.measure_gridinfo_faster(0, 10 ** 9)
+    assert_b_close(out["B"], b1, 2e-6, 2e-7)
+    assert np.array_equal(out["N"], g1["N_tri"])
+    np.testing.assert_allclose(out["K"], g1["k_mean"], rtol=1e-12)
