@@ -528,3 +528,24 @@ def test_two_gpu_run_matches_single_gpu(bk, syn, tmp_path):
     assert_b_close(out["B"], b1, 2e-6, 2e-7)
     assert np.array_equal(out["N"], g1["N_tri"])
     np.testing.assert_allclose(out["K"], g1["k_mean"], rtol=1e-12)
+
+
+def test_non_cubic_box_gpu(bk, syn):
+    n = 48
+    box = np.array([1000.0, 800.0, 1200.0])
+    kf = 2 * np.pi / box.max()
+    mesh = syn.lognormal_mesh(n, seed=6, dtype=np.float64)
+    kw = dict(kmin=0.6 * kf, kmax=9.1 * kf, dk=1.1 * kf)
+    edges = orc.bin_edges(**kw)
+    _, idx = orc.triangles_all(edges, 1)
+    want = orc.measure_unnormalized([mesh], box, edges, idx, workers=4)
+    wn, wk = orc.measure_gridinfo(n, box, edges, idx, workers=4)
+    for grid in ("full", "auto"):
+        fb = bk.FFTBispectrum(mesh, BoxSize=box, grid=grid, **kw)
+        got = fb.measure_bispectrum_faster()["B"]
+        gi = fb.measure_gridinfo_faster()
+        assert_b_close(got, want, 1e-10, 1e-12)
+        assert np.array_equal(gi["N_tri"], np.rint(wn))
+        ok = wn > 0.5
+        np.testing.assert_allclose(gi["k_mean"][ok], wk[ok], rtol=1e-10)
+        fb.close()

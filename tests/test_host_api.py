@@ -144,3 +144,28 @@ def test_subbox_helpers_and_subbox_gridinfo_golden(tmp_path):
         else:
             assert fmt_e(r["N_tri"][t]) == fmt_e(g[t, 10])
             assert [fmt_e(v) for v in r["k_mean"][t]] == [fmt_e(v) for v in g[t, 1:4]]
+
+
+def test_non_cubic_box_and_dtype_override():
+    """BoxSize with three different side lengths: per-axis wavenumber tables and the crop radius
+    (from the longest side) must reproduce the oracle; compute_dtype overrides the mesh dtype."""
+    n = 16
+    box = np.array([200.0, 160.0, 240.0])
+    kf = 2 * np.pi / box.max()
+    mesh = _mesh(n, 9)
+    fb = bk.FFTBispectrum(mesh, BoxSize=box, kmin=0.6 * kf, kmax=5.1 * kf, dk=1.1 * kf,
+                          device=torch.device("cpu"))
+    edges = orc.bin_edges(0.6 * kf, 5.1 * kf, 1.1 * kf)
+    _, idx = orc.triangles_all(edges, 1)
+    r = fb.measure_bispectrum_faster()
+    g = fb.measure_gridinfo_faster()
+    want = orc.measure_unnormalized([mesh], box, edges, idx)
+    wn, wk = orc.measure_gridinfo(n, box, edges, idx)
+    np.testing.assert_allclose(r["B"], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    assert np.array_equal(g["N_tri"], np.rint(wn))
+    ok = wn > 0.5
+    np.testing.assert_allclose(g["k_mean"][ok], wk[ok], rtol=1e-10)
+    assert fb._meas().precision == bkmain.F64
+    fb32 = bk.FFTBispectrum(mesh, BoxSize=box, kmin=0.6 * kf, kmax=5.1 * kf, dk=1.1 * kf,
+                            compute_dtype=np.float32, device=torch.device("cpu"))
+    assert fb32._meas().precision == bkmain.F32
