@@ -418,6 +418,14 @@ class Engine:
     def release_scratch(self):
         self._scratch = None
 
+    def set_chunk(self, nsh):
+        """Change how many shells are synthesised per call (the scratch scales with it)."""
+        self.chunk = int(max(1, min(nsh, self.chunk)))
+        self._scratch = None
+        self._row_cap = None
+        if self.device.type == "cuda":
+            torch.cuda.empty_cache()
+
     def row_capacity(self):
         """How many shell fields ([ncells] of the storage dtype) fit in device memory next to
         the synthesis scratch.  `max_rows` (tests) overrides the measurement."""
@@ -571,6 +579,9 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
     """
     njobs = len(job_seg_off)
     out = np.empty((njobs, len(uniq)))
+    nbins_all = len(np.unique(uniq))
+    if engine.row_capacity() // nseg < nbins_all and engine.chunk > 1 and engine.max_rows is None:
+        engine.set_chunk(1)      # trade synthesis batching for field memory before cutting the list
     seg_cap = max(1, engine.row_capacity() // nseg)       # distinct bins resident per segment
     if int(uniq.max()) + 1 <= seg_cap or len(np.unique(uniq)) <= seg_cap:
         batches = [np.arange(len(uniq))]              # the common case: everything is resident

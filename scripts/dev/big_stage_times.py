@@ -1,6 +1,6 @@
 """Dev: per-stage times of one shell + a 3-row contraction at 2048^3 (S=300 binning)."""
 import os, sys, time
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+# (expandable_segments makes 100+ GiB allocations take tens of seconds: not used)
 import numpy as np, torch
 sys.path.insert(0, ".")
 from bskit_b200 import engine as eng, _native as nat, synthetic as syn

@@ -2,7 +2,7 @@
 Each rank generates its own white-noise slab on the device.  Prints per-stage times (max over
 ranks) for the forward transform, the equilateral and the squeezed measurement."""
 import os, sys, time
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+# (expandable_segments makes 100+ GiB allocations take tens of seconds: not used)
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, ".")
 import bskit_b200 as bk

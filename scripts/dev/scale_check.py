@@ -1,7 +1,7 @@
 """Dev: capacity / overflow check at 1024^3 (all triangles, forces batches on one GPU) and
 2048^3 (equilateral + squeezed).  White-noise device-generated meshes; prints stage times."""
 import os, sys, time
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+# (expandable_segments makes 100+ GiB allocations take tens of seconds: not used)
 import numpy as np, torch
 sys.path.insert(0, ".")
 import bskit_b200 as bk
