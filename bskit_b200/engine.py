@@ -353,8 +353,12 @@ class Engine:
         (N,N,N) array (numpy / torch, any device) or already the local slab."""
         n, f = self.grid.nmesh, self.info
         if isinstance(mesh, np.ndarray):
+            if tuple(mesh.shape) == (n, n, n):
+                mesh = mesh[f.nx0:f.nx0 + f.nxl]          # slice first: memory-mapped files stay lazy
             if mesh.dtype not in (np.float32, np.float64):
                 mesh = mesh.astype(np.float64)
+            if not mesh.flags.writeable:                  # e.g. np.load(mmap_mode='r')
+                mesh = np.array(mesh)
             t = torch.from_numpy(mesh)
         else:
             t = mesh

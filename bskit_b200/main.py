@@ -47,7 +47,7 @@ __all__ = [
     "number_field", "k_field", "pk_FFT", "compute_Nbin", "compute_k_means_on_grid",
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
     "combine_gridinfo_and_unnormalized", "clear_cache",
-    "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm",
+    "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "downsample_mesh",
 ]
 
 F32, F64 = 0, 1
@@ -412,6 +412,33 @@ def field_subbox_pm(box_multiindex, nsub_per_side, source):
     sub = mesh.array[i0[0]:i0[0] + ns, i0[1]:i0[1] + ns, i0[2]:i0[2] + ns]
     sub = np.ascontiguousarray(sub) if isinstance(sub, np.ndarray) else sub.contiguous()
     return ArrayMesh(sub, mesh.attrs["BoxSize"] / float(nsub_per_side), compensation=mesh.compensation)
+
+
+def downsample_mesh(mesh, Nmesh_new, device=None):
+    """Fourier-space downsampling of a density mesh to ``Nmesh_new``^3 on the GPU: forward
+    transform, keep the modes with |n_axis| < Nmesh_new/2, inverse transform on the coarse grid
+    (what ``scripts/grids/downsample_bigfile_grid.py:46`` does through nbodykit's
+    ``mesh.paint(mode='real', Nmesh=...)``; the mean is preserved).  Returns an :class:`ArrayMesh`
+    holding a float64 numpy array."""
+    import torch
+    from . import _native as nat
+    from . import engine as eng
+    src = _as_mesh(mesh)
+    n, m = int(src.attrs["Nmesh"][0]), int(Nmesh_new)
+    if m % 2 or m > n or m < 4:
+        raise ValueError("Nmesh_new must be even, >= 4 and <= Nmesh")
+    if m == n:
+        return src
+    grid = eng.GridChoice(n, m, m // 2 - 1, False)
+    e = eng.Engine(grid, src.attrs["BoxSize"], nat.F64, device=device)
+    try:
+        cube = e.forward(src.array, _Session(n, src.attrs["BoxSize"]).compensation_tables(e, src.compensation))
+        out = torch.empty((1, e.ncells), dtype=e.rdtype, device=e.device)
+        e.synthesize(cube, nat.KIND_DATA, 0.0, np.array([0.0]), np.array([1e300]), out)
+        arr = out.reshape(e.info.mxl, m, m).cpu().numpy()
+    finally:
+        e.close()
+    return ArrayMesh(arr, src.attrs["BoxSize"])
 
 
 def combine_gridinfo_and_unnormalized(bin_info, b_vals, k_max=np.inf, tol=0.01):

@@ -49,6 +49,11 @@ class ArrayMesh:
                       "Nmesh": np.array([shape[1]] * 3, dtype=np.int64)}
         self.compensation = compensation
 
+    @classmethod
+    def from_npy(cls, path, BoxSize, mmap=True):
+        """A mesh stored as a .npy array (cf. scripts/grids/convert_npy_grid_to_bigfile.py)."""
+        return cls(np.load(path, mmap_mode="r" if mmap else None), BoxSize)
+
     def apply(self, func, kind="circular", mode="complex"):
         """Queue a k-space action like nbodykit's ``mesh.apply``.  Only the CIC
         compensation object is supported (the one action the reference's scripts use)."""

@@ -21,4 +21,4 @@ print("BF16 matmul 8192^3: %.0f TFLOP/s" % bench(lambda: xb @ yb, 2 * n ** 3))
 xd = torch.randn(4096, 4096, device=dev, dtype=torch.float64); yd = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
 print("FP64 matmul 4096^3: %.1f TFLOP/s" % bench(lambda: xd @ yd, 2 * 4096 ** 3, 3))
 a = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev); b = torch.empty_like(a)
-print("copy 2 GiB: %.0f GB/s" % (bench(lambda: b.copy_(a), 2 * a.numel() * 2) ))
+print("copy 2 GiB (read+write): %.0f GB/s" % (1e3 * bench(lambda: b.copy_(a), 2 * a.numel() * 2)))
