@@ -109,7 +109,8 @@ template <typename T>
 __global__ void shell_filter_kernel(const double2* __restrict__ cube,  // [Kx][Ky][Kz] float64
                                     typename Cx<T>::type* __restrict__ xcols,  // [M][nsh][Ky][Kz]
                                     int Kx, int Ky, int Kz, int N, int M, int nsh, int kind,
-                                    double kpow, BinEdges bins, const double* __restrict__ kxt,
+                                    double kpow, int ky_inner, BinEdges bins,
+                                    const double* __restrict__ kxt,
                                     const double* __restrict__ kyt,
                                     const double* __restrict__ kzt) {
   const int64_t plane = (int64_t)Ky * Kz;
@@ -139,7 +140,10 @@ __global__ void shell_filter_kernel(const double2* __restrict__ cube,  // [Kx][K
     typename Cx<T>::type zero;
     zero.x = (T)0;
     zero.y = (T)0;
-    typename Cx<T>::type* dst = xcols + (int64_t)mx * nsh * plane + rem;
+    // inner layout [ky][kz] for the generic path, [kz][ky] (ky contiguous) for the pruned path,
+    // whose y-scatter then reads and writes contiguous runs
+    typename Cx<T>::type* dst =
+        xcols + (int64_t)mx * nsh * plane + (ky_inner ? (int64_t)jz * Ky + jy : rem);
 #pragma unroll 4
     for (int s = 0; s < nsh; ++s) {
       bool in = (kk <= bins.hi[s]) & (kk >= bins.lo[s]);
@@ -315,8 +319,8 @@ static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int
   if (f.kx != M)  // rows of the padded x axis that no kept mode maps to must be zero
     BSK_CUDA(cudaMemsetAsync(xcols, 0, sizeof(C) * (size_t)xc, p->stream));
   shell_filter_kernel<TF><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-      (const double2*)cube, (C*)xcols, (int)f.kx, (int)f.ky, (int)f.kz, N, M, nsh, kind, kpow, be,
-      p->d_kx, p->d_ky, p->d_kz);
+      (const double2*)cube, (C*)xcols, (int)f.kx, (int)f.ky, (int)f.kz, N, M, nsh, kind, kpow,
+      p->use_zpass ? 1 : 0, be, p->d_kx, p->d_ky, p->d_kz);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   cufftHandle hx, h2;

@@ -16,7 +16,8 @@ namespace bsk {
 
 using zfft::cplx;
 
-// [x][nsh][Ky][Kz] (after the x transform) -> [nsh][mxl][Kz][M]  (y contiguous, zero padded)
+// [x][nsh][Kz][Ky] (after the x transform; ky contiguous) -> [nsh][mxl][Kz][M]  (y contiguous,
+// zero padded): contiguous reads and writes
 __global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __restrict__ ycols,
                                  int M, int Ky, int Kz, int nsh, int mx0, int mxl) {
   const int nc = (Ky - 1) / 2;
@@ -35,7 +36,7 @@ __global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __r
     else if (iy >= M - nc) jy = iy - M + Ky;
     else jy = -1;
     double2 v = make_double2(0.0, 0.0);
-    if (jy >= 0) v = xcols[(((int64_t)(mx0 + xl) * nsh + s) * Ky + jy) * Kz + kz];
+    if (jy >= 0) v = xcols[(((int64_t)(mx0 + xl) * nsh + s) * Kz + kz) * Ky + jy];
     ycols[i] = v;
   }
 }
