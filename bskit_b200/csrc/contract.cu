@@ -395,6 +395,8 @@ tri_stream_reduce_kernel(const T* const* __restrict__ rowptr, const int* __restr
 
 }  // namespace bsk
 
+#include "contract_tc.cuh"
+
 // split each block's tile over `split` threads so that a round fills the CTA
 static int choose_split(int nblocks, int threads) {
   int best = 1;
@@ -426,6 +428,12 @@ struct bsk_cplan {
   size_t smem_limit = 0;
   std::vector<const void*> last_rowptr;  // what d_rowptr currently holds
   std::vector<int> last_joboff;          // what d_joboff currently holds
+  // tensor-core schedule (contract_tc.cuh); tc_units == 0: list not eligible
+  int tc_units = 0, tc_nu0 = 0, tc_nu1 = 0, tc_ncols = 0;
+  int tc_col0[8] = {0}, tc_ncol[8] = {0};
+  uint32_t* d_tc_slots = nullptr;
+  int* d_tc_tri_slot = nullptr;
+  double* d_tc_partial = nullptr;
 };
 
 using namespace bsk;
@@ -469,6 +477,139 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   return BSK_OK;
 }
 
+// Tensor-core schedule: every triangle (a <= b <= c after sorting its rows) reads entry
+// D[pair(a,b)][c].  Pair rows are laid out so that the lane that generates a pair already holds
+// one of its two rows in registers ("resident"): lane v of every warp owns row v < 32, and
+// "slot" s = 0..16 pairs it with row (v + s) mod 32, which covers every pair of rows < 32 once;
+// rows >= 32 get one slot each (warp-uniform partner), pairs among rows >= 32 are packed into
+// slots that load both rows.  Four slots (one per TMEM lane quarter) form a 128-row unit.
+static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows) {
+  using namespace bsk::tc;
+  if (nrows > MAXR || ntri < 256) return false;
+  const int R = nrows;
+  std::vector<char> need((size_t)R * R, 0);
+  std::vector<int> ta((size_t)ntri), tb((size_t)ntri), tcc((size_t)ntri);
+  for (int t = 0; t < ntri; ++t) {
+    int r[3] = {rows[3 * t], rows[3 * t + 1], rows[3 * t + 2]};
+    std::sort(r, r + 3);
+    ta[t] = r[0]; tb[t] = r[1]; tcc[t] = r[2];
+    need[(size_t)r[0] * R + r[1]] = 1;
+  }
+  struct Slot { uint32_t e[32]; bool used; };
+  const uint32_t idle = (uint32_t)R | ((uint32_t)R << 8);
+  auto fresh = [&](bool resident) { Slot s; for (auto& x : s.e) x = idle | (resident ? 1u << 16 : 0u); s.used = false; return s; };
+  std::vector<Slot> circ(17, fresh(true)), high, loose;
+  std::vector<int> pair_slot((size_t)R * R, -1), pair_lane((size_t)R * R, -1);   // slot ids resolved below
+  // ids: circ s -> s; high b -> 100 + (b - 32); loose k -> 200 + k
+  for (int b = 32; b < R; ++b) high.push_back(fresh(true));
+  int loose_fill = 32;
+  for (int a = 0; a < R; ++a)
+    for (int b = a; b < R; ++b) {
+      if (!need[(size_t)a * R + b]) continue;
+      int sid, lane;
+      uint32_t e;
+      if (b < 32) {
+        const int d = b - a;
+        if (d <= 16) { sid = d; lane = a; e = (uint32_t)a | ((uint32_t)b << 8) | (1u << 16); }
+        else { sid = 32 - d; lane = b; e = (uint32_t)b | ((uint32_t)a << 8) | (1u << 16); }
+        circ[sid].e[lane] = e; circ[sid].used = true;
+      } else if (a < 32) {
+        sid = 100 + (b - 32); lane = a;
+        high[b - 32].e[lane] = (uint32_t)a | ((uint32_t)b << 8) | (1u << 16); high[b - 32].used = true;
+      } else {
+        if (loose_fill == 32) { loose.push_back(fresh(false)); loose_fill = 0; }
+        sid = 200 + (int)loose.size() - 1; lane = loose_fill++;
+        loose.back().e[lane] = (uint32_t)a | ((uint32_t)b << 8); loose.back().used = true;
+      }
+      pair_slot[(size_t)a * R + b] = sid;
+      pair_lane[(size_t)a * R + b] = lane;
+    }
+  // column range [cmin, cmax] each slot needs, from the triangles that read it
+  std::unordered_map<int, std::pair<int, int>> range;
+  for (int t = 0; t < ntri; ++t) {
+    const int sid = pair_slot[(size_t)ta[t] * R + tb[t]];
+    auto it = range.find(sid);
+    if (it == range.end()) range[sid] = {tcc[t], tcc[t]};
+    else { it->second.first = std::min(it->second.first, tcc[t]); it->second.second = std::max(it->second.second, tcc[t]); }
+  }
+  struct SlotRef { int sid; const Slot* s; int cmin, cmax; };
+  std::vector<SlotRef> order;
+  for (int s = 0; s < 17; ++s) if (circ[s].used) order.push_back({s, &circ[s], range[s].first, range[s].second});
+  for (size_t k = 0; k < high.size(); ++k) if (high[k].used) order.push_back({100 + (int)k, &high[k], range[100 + (int)k].first, range[100 + (int)k].second});
+  for (size_t k = 0; k < loose.size(); ++k) order.push_back({200 + (int)k, &loose[k], range[200 + (int)k].first, range[200 + (int)k].second});
+  std::stable_sort(order.begin(), order.end(), [](const SlotRef& x, const SlotRef& y) { return x.cmin / 8 < y.cmin / 8; });
+  const int nunits = ((int)order.size() + 3) / 4;
+  if (nunits < 1 || nunits > 2 * UPT) return false;
+  struct Unit { int first, count, col0, ncol; };
+  std::vector<Unit> units;
+  for (int u = 0; u < nunits; ++u) {
+    Unit un{u * 4, std::min(4, (int)order.size() - u * 4), 1 << 30, 0};
+    int cmax = 0;
+    for (int k = 0; k < un.count; ++k) { un.col0 = std::min(un.col0, order[un.first + k].cmin / 8 * 8); cmax = std::max(cmax, order[un.first + k].cmax); }
+    un.ncol = (cmax + 8) / 8 * 8 - un.col0;
+    units.push_back(un);
+  }
+  // widest units first, dealt alternately to the two teams; position j must fit cap(j)
+  std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.ncol > y.ncol; });
+  const int ncols = (R + 7) / 8 * 8;
+  const int nu0 = (nunits + 1) / 2, nu1 = nunits - nu0;
+  std::vector<uint32_t> tab((size_t)2 * UPT * 128, idle | (1u << 16));
+  std::unordered_map<int, int> slot_pos;   // slot id -> (team * UPT + j) * 4 + q
+  for (int u = 0; u < nunits; ++u) {
+    const int team = u & 1, j = u >> 1;
+    if (units[u].ncol > cap(j)) return false;
+    cp->tc_col0[team * UPT + j] = units[u].col0;
+    cp->tc_ncol[team * UPT + j] = units[u].ncol;
+    for (int k = 0; k < units[u].count; ++k) {
+      const SlotRef& sr = order[units[u].first + k];
+      const int pos = (team * UPT + j) * 4 + k;
+      slot_pos[sr.sid] = pos;
+      for (int l = 0; l < 32; ++l) tab[(size_t)pos * 32 + l] = sr.s->e[l];
+    }
+  }
+  std::vector<int> tri_slot((size_t)ntri);
+  for (int t = 0; t < ntri; ++t) {
+    const size_t pi = (size_t)ta[t] * R + tb[t];
+    const int pos = slot_pos[pair_slot[pi]], lane = pair_lane[pi];
+    const int q = pos % 4, tj = pos / 4, team = tj / UPT, j = tj % UPT;
+    tri_slot[t] = (capoff(j) + tcc[t] - cp->tc_col0[tj]) * 256 + team * 128 + q * 32 + lane;
+  }
+  cp->tc_units = nunits; cp->tc_nu0 = nu0; cp->tc_nu1 = nu1; cp->tc_ncols = ncols;
+  if (cudaMalloc((void**)&cp->d_tc_slots, sizeof(uint32_t) * tab.size()) != cudaSuccess) return false;
+  cudaMemcpy(cp->d_tc_slots, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice);
+  if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int) * (size_t)ntri) != cudaSuccess) return false;
+  cudaMemcpy(cp->d_tc_tri_slot, tri_slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice);
+  const size_t stride = (size_t)CAPSUM * 256;
+  if (cudaMalloc((void**)&cp->d_tc_partial, sizeof(double) * stride * cp->sm_count) != cudaSuccess) return false;
+  return true;
+}
+
+static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStream_t st) {
+  using namespace bsk::tc;
+  Params p;
+  p.rowptr = (const float* const*)cp->d_rowptr;
+  p.nrows = cp->nrows;
+  p.ncols = cp->tc_ncols;
+  p.ntiles = ncells / TL;
+  p.nu0 = cp->tc_nu0;
+  p.nu1 = cp->tc_nu1;
+  p.slot_tab = cp->d_tc_slots;
+  p.partial = cp->d_tc_partial;
+  p.partial_stride = (int64_t)CAPSUM * 256;
+  for (int i = 0; i < 2 * UPT; ++i) { p.ucol0[i] = cp->tc_col0[i]; p.uncol[i] = cp->tc_ncol[i]; }
+  p.flush_chunks = 512;
+  const int ncta = (int)std::min<int64_t>(p.ntiles, cp->sm_count);
+  BSK_CUDA(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0, sizeof(double) * (size_t)ncta * p.partial_stride, st));
+  tc_contract_kernel<<<ncta, NTHREADS, SMEM_BYTES, st>>>(p);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  fold_partials_kernel<<<(int)std::min<int64_t>((cp->ntri + 127) / 128, 148 * 8), 128, 0, st>>>(
+      cp->d_tc_partial, p.partial_stride, ncta, 1, cp->ntri, 0, cp->d_tc_tri_slot, sums);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
+  return BSK_OK;
+}
 
 extern "C" {
 
@@ -531,6 +672,7 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
   BSK_CUDA(cudaMallocHost((void**)&cp->h_rowptr, sizeof(void*) * (size_t)nrows));
   BSK_CUDA(cudaMalloc((void**)&cp->d_joboff, sizeof(int) * 3 * (size_t)max_jobs));
   BSK_CUDA(cudaMallocHost((void**)&cp->h_joboff, sizeof(int) * 3 * (size_t)max_jobs));
+  if (!build_tc_schedule(cp, ntri, rows, nrows)) cp->tc_units = 0;
   *out = cp;
   return BSK_OK;
 }
@@ -544,6 +686,9 @@ int bsk_cplan_destroy(bsk_cplan* cp) {
   cudaFreeHost(cp->h_rowptr);
   cudaFree(cp->d_joboff);
   cudaFreeHost(cp->h_joboff);
+  cudaFree(cp->d_tc_slots);
+  cudaFree(cp->d_tc_tri_slot);
+  cudaFree(cp->d_tc_partial);
   delete cp;
   return BSK_OK;
 }
@@ -597,8 +742,12 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
   }
   if (precision == BSK_F64) return contract_impl<double, double, 0>(cp, ncells, njobs, sums, st);
   if (accum_precision == BSK_F64) return contract_impl<float, double, 0>(cp, ncells, njobs, sums, st);
-  static const char* mode = getenv("BSK_CONTRACT_MODE");   // A/B timing knob: 0 scalar FFMA, 1 packed FFMA2
+  // A/B knob: 0 scalar FFMA, 1 packed FFMA2, 2 tcgen05 (3xTF32) when the list is eligible
+  const char* mode = getenv("BSK_CONTRACT_MODE");
   const int m = mode ? atoi(mode) : 1;
+  if (m == 2 && cp->tc_units > 0 && njobs == 1 && jo[0] == 0 && jo[1] == 0 && jo[2] == 0 &&
+      ncells % bsk::tc::TL == 0)
+    return contract_tc_impl(cp, ncells, sums, st);
   if (m == 0) return contract_impl<float, float, 0>(cp, ncells, njobs, sums, st);
   return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
 }
