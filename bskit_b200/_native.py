@@ -20,7 +20,8 @@ MAX_CHUNK = 64
 EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
     "bsk_set_compensation", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
-    "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_contract",
+    "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_cplan_set_path",
+    "bsk_cplan_path", "bsk_contract",
     "bsk_reduce_list", "bsk_launch_count",
 )
 
@@ -71,6 +72,8 @@ def lib():
     L.bsk_cplan_create.argtypes = [C.POINTER(vp), ip, C.POINTER(C.c_int32), ip, ip]
     L.bsk_cplan_destroy.argtypes = [vp]
     L.bsk_cplan_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.bsk_cplan_set_path.argtypes = [vp, ip]
+    L.bsk_cplan_path.argtypes = [vp, C.POINTER(C.c_int64)]
     L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     L.bsk_reduce_list.argtypes = [C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     for name in EXPORTS:

@@ -429,8 +429,11 @@ struct bsk_cplan {
   std::vector<const void*> last_rowptr;  // what d_rowptr currently holds
   std::vector<int> last_joboff;          // what d_joboff currently holds
   // tensor-core schedule (contract_tc.cuh); tc_units == 0: list not eligible
-  int tc_units = 0, tc_nu0 = 0, tc_nu1 = 0, tc_ncols = 0;
-  int tc_col0[8] = {0}, tc_ncol[8] = {0};
+  int tc_units = 0, tc_ncols = 0;
+  int path = 0;        // requested: 0 FP32-pipe tile kernel, 1 tensor cores when the call is eligible
+  int last_path = 0;   // what the most recent bsk_contract call ran
+  int tc_nu[bsk::tc::NTEAMS] = {0};
+  int tc_col0[bsk::tc::NTEAMS * bsk::tc::UPT] = {0}, tc_ncol[bsk::tc::NTEAMS * bsk::tc::UPT] = {0};
   uint32_t* d_tc_slots = nullptr;
   int* d_tc_tri_slot = nullptr;
   double* d_tc_partial = nullptr;
@@ -539,7 +542,7 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
   for (size_t k = 0; k < loose.size(); ++k) order.push_back({200 + (int)k, &loose[k], range[200 + (int)k].first, range[200 + (int)k].second});
   std::stable_sort(order.begin(), order.end(), [](const SlotRef& x, const SlotRef& y) { return x.cmin / 8 < y.cmin / 8; });
   const int nunits = ((int)order.size() + 3) / 4;
-  if (nunits < 1 || nunits > 2 * UPT) return false;
+  if (nunits < 1 || nunits > NTEAMS * UPT) return false;
   struct Unit { int first, count, col0, ncol; };
   std::vector<Unit> units;
   for (int u = 0; u < nunits; ++u) {
@@ -552,12 +555,13 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
   // widest units first, dealt alternately to the two teams; position j must fit cap(j)
   std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.ncol > y.ncol; });
   const int ncols = (R + 7) / 8 * 8;
-  const int nu0 = (nunits + 1) / 2, nu1 = nunits - nu0;
-  std::vector<uint32_t> tab((size_t)2 * UPT * 128, idle | (1u << 16));
+  std::vector<uint32_t> tab((size_t)NTEAMS * UPT * 128, idle);
+  for (int t = 0; t < NTEAMS; ++t) cp->tc_nu[t] = 0;
   std::unordered_map<int, int> slot_pos;   // slot id -> (team * UPT + j) * 4 + q
   for (int u = 0; u < nunits; ++u) {
-    const int team = u & 1, j = u >> 1;
+    const int team = u % NTEAMS, j = u / NTEAMS;
     if (units[u].ncol > cap(j)) return false;
+    cp->tc_nu[team] = j + 1;
     cp->tc_col0[team * UPT + j] = units[u].col0;
     cp->tc_ncol[team * UPT + j] = units[u].ncol;
     for (int k = 0; k < units[u].count; ++k) {
@@ -572,14 +576,14 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
     const size_t pi = (size_t)ta[t] * R + tb[t];
     const int pos = slot_pos[pair_slot[pi]], lane = pair_lane[pi];
     const int q = pos % 4, tj = pos / 4, team = tj / UPT, j = tj % UPT;
-    tri_slot[t] = (capoff(j) + tcc[t] - cp->tc_col0[tj]) * 256 + team * 128 + q * 32 + lane;
+    tri_slot[t] = (capoff(j) + tcc[t] - cp->tc_col0[tj]) * NTEAMTHREADS + team * 128 + q * 32 + lane;
   }
-  cp->tc_units = nunits; cp->tc_nu0 = nu0; cp->tc_nu1 = nu1; cp->tc_ncols = ncols;
+  cp->tc_units = nunits; cp->tc_ncols = ncols;
   if (cudaMalloc((void**)&cp->d_tc_slots, sizeof(uint32_t) * tab.size()) != cudaSuccess) return false;
   cudaMemcpy(cp->d_tc_slots, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice);
   if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int) * (size_t)ntri) != cudaSuccess) return false;
   cudaMemcpy(cp->d_tc_tri_slot, tri_slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice);
-  const size_t stride = (size_t)CAPSUM * 256;
+  const size_t stride = (size_t)CAPSUM * NTEAMTHREADS;
   if (cudaMalloc((void**)&cp->d_tc_partial, sizeof(double) * stride * cp->sm_count) != cudaSuccess) return false;
   return true;
 }
@@ -591,19 +595,37 @@ static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStr
   p.nrows = cp->nrows;
   p.ncols = cp->tc_ncols;
   p.ntiles = ncells / TL;
-  p.nu0 = cp->tc_nu0;
-  p.nu1 = cp->tc_nu1;
+  for (int t = 0; t < NTEAMS; ++t) p.nu[t] = cp->tc_nu[t];
   p.slot_tab = cp->d_tc_slots;
   p.partial = cp->d_tc_partial;
-  p.partial_stride = (int64_t)CAPSUM * 256;
-  for (int i = 0; i < 2 * UPT; ++i) { p.ucol0[i] = cp->tc_col0[i]; p.uncol[i] = cp->tc_ncol[i]; }
+  p.partial_stride = (int64_t)CAPSUM * NTEAMTHREADS;
+  for (int i = 0; i < NTEAMS * UPT; ++i) { p.ucol0[i] = cp->tc_col0[i]; p.uncol[i] = cp->tc_ncol[i]; }
   p.flush_chunks = 512;
+  p.prof = nullptr;
+#if BSK_TC_PROF
+  static long long* d_prof = nullptr;
+  if (!d_prof) cudaMalloc((void**)&d_prof, 8 * 8 * sizeof(long long));
+  cudaMemsetAsync(d_prof, 0, 8 * 8 * sizeof(long long), st);
+  p.prof = d_prof;
+#endif
   const int ncta = (int)std::min<int64_t>(p.ntiles, cp->sm_count);
   BSK_CUDA(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0, sizeof(double) * (size_t)ncta * p.partial_stride, st));
   tc_contract_kernel<<<ncta, NTHREADS, SMEM_BYTES, st>>>(p);
   count_launch();
   BSK_CUDA(cudaGetLastError());
+#if BSK_TC_PROF
+  {
+    long long h[64];
+    cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int t = 0; t < NTEAMS; ++t)
+      fprintf(stderr, "tc prof team %d: units %lld | per unit: raw %.0f gen %.0f a_empty %.0f st+arrive %.0f d_full %.0f drain %.0f\n", t,
+              h[t * 8 + 6], (double)h[t * 8] / h[t * 8 + 6], (double)h[t * 8 + 1] / h[t * 8 + 6], (double)h[t * 8 + 2] / h[t * 8 + 6],
+              (double)h[t * 8 + 3] / h[t * 8 + 6], (double)h[t * 8 + 4] / h[t * 8 + 6], (double)h[t * 8 + 5] / h[t * 8 + 6]);
+    const long long* m = h + NTEAMS * 8;
+    fprintf(stderr, "tc prof mma: total %lld cycles: a_full %lld d_empty %lld issue %lld b_full %lld\n", m[4], m[0], m[1], m[2], m[3]);
+  }
+#endif
   fold_partials_kernel<<<(int)std::min<int64_t>((cp->ntri + 127) / 128, 148 * 8), 128, 0, st>>>(
       cp->d_tc_partial, p.partial_stride, ncta, 1, cp->ntri, 0, cp->d_tc_tri_slot, sums);
   count_launch();
@@ -702,6 +724,20 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]) {
   return BSK_OK;
 }
 
+int bsk_cplan_set_path(bsk_cplan* cp, int path) {
+  BSK_REQUIRE(cp && (path == 0 || path == 1), "bsk_cplan_set_path: path must be 0 (FP32 pipe) or 1 (tensor cores)");
+  cp->path = path;
+  return BSK_OK;
+}
+
+int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]) {
+  BSK_REQUIRE(cp && out, "bsk_cplan_path: null argument");
+  out[0] = cp->tc_units;
+  out[1] = cp->path;
+  out[2] = cp->last_path;
+  return BSK_OK;
+}
+
 int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int accum_precision,
                  int64_t ncells, int njobs, const int32_t* job_off, double* sums,
                  void* cuda_stream) {
@@ -745,9 +781,12 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
   // A/B knob: 0 scalar FFMA, 1 packed FFMA2, 2 tcgen05 (3xTF32) when the list is eligible
   const char* mode = getenv("BSK_CONTRACT_MODE");
   const int m = mode ? atoi(mode) : 1;
-  if (m == 2 && cp->tc_units > 0 && njobs == 1 && jo[0] == 0 && jo[1] == 0 && jo[2] == 0 &&
-      ncells % bsk::tc::TL == 0)
+  cp->last_path = 0;
+  if ((m == 2 || cp->path == 1) && cp->tc_units > 0 && njobs == 1 && jo[0] == 0 && jo[1] == 0 && jo[2] == 0 &&
+      ncells % bsk::tc::TL == 0) {
+    cp->last_path = 1;
     return contract_tc_impl(cp, ncells, sums, st);
+  }
   if (m == 0) return contract_impl<float, float, 0>(cp, ncells, njobs, sums, st);
   return contract_impl<float, float, 1>(cp, ncells, njobs, sums, st);
 }

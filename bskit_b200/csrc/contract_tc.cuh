@@ -14,14 +14,14 @@
 // accumulator (round toward zero, profiles/r1_tensor_core_rounding_probe.txt), which would bias a
 // long heavily-cancelling sum, so an accumulator lives in TMEM for ONE 32-cell chunk only
 // (12 MMAs); it is then drained into fp32 registers with round-to-nearest adds, and those are
-// flushed into float64 partials every few hundred chunks.
+// flushed into float64 partials every few hundred chunks.  Measured: 3.5e-7 of max|sum| against
+// a float64 reference (FP32-pipe kernel: 5e-8).
 //
-// Roles (384 threads, one CTA per SM, persistent over tiles of 128 cells):
-//   warps 0-3 / 4-7  two generator+drain teams; lane v of every warp keeps row v of the current
-//                    chunk in registers, so a unit costs one 128-byte shared-memory read per lane
-//   warp 8           TMA producer: raw [row][cell] tiles, cp.async.bulk + mbarrier
-//   warp 9           MMA issuer (one elected lane)
-//   warps 10-11      convert the raw tile to the B operand images (hi / lo, K-major core
+// Roles (one CTA per SM, persistent over tiles of 128 cells):
+//   NTEAMS x 4 warps generator+drain teams; warp q of a team owns TMEM lanes [32q, 32q+32)
+//   1 warp           TMA producer: raw [row][cell] tiles, cp.async.bulk + mbarrier
+//   1 warp           MMA issuer (one elected lane)
+//   2 warps          convert the raw tile to the B operand images (hi / lo, K-major core
 //                    matrices: 8 rows x 16 bytes)
 #pragma once
 
@@ -32,14 +32,25 @@ constexpr int CH = 32;            // cells per chunk = K extent of one unit
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
 constexpr int MAXR = 40;          // rows (N <= 40)
-constexpr int UPT = 4;            // units per team (2 teams -> at most 8 units = 1024 pair rows)
+constexpr int NTEAMS = 3;
+constexpr int UPT = 3;            // units per team (NTEAMS * UPT * 128 pair rows at most)
+constexpr int NTEAMTHREADS = NTEAMS * 128;
+constexpr int NTHREADS = NTEAMTHREADS + 128;
+#ifndef BSK_TC_PROF
+#define BSK_TC_PROF 0
+#endif
+constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
+constexpr int REGS_TEAM = 144, REGS_AUX = 80;      // 384*144 + 128*80 = 512*128
+static_assert(NTEAMTHREADS * REGS_TEAM + 128 * REGS_AUX <= NTHREADS * (65536 / NTHREADS / 8 * 8), "register split");
 // D columns a unit may need, by position j in its team (units are dealt to the teams in order of
 // decreasing width): a pair (a <= b) only meets rows c >= b, so most units need few columns
-__host__ __device__ constexpr int cap(int j) { return j == 0 ? 40 : j == 1 ? 32 : j == 2 ? 24 : 8; }
-__host__ __device__ constexpr int capoff(int j) { return j == 0 ? 0 : j == 1 ? 40 : j == 2 ? 72 : 96; }
-constexpr int CAPSUM = 104;
-constexpr int NTHREADS = 384;
-constexpr bool USE_OWN = false;   // keep lane v's row v in registers (saves shared-memory reads, costs 32 registers)
+__host__ __device__ constexpr int cap(int j) { return j == 0 ? 40 : j == 1 ? 32 : 8; }
+__host__ __device__ constexpr int capoff(int j) { return j == 0 ? 0 : j == 1 ? 40 : 72; }
+constexpr int CAPSUM = 80;
+// TMEM columns: one accumulator per team, two A buffers (hi 32 + lo 32 columns) per team
+constexpr int TM_D = 0, TM_A = 128;
+static_assert(NTEAMS * MAXR <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
+
 constexpr int RAW_STRIDE = TL * 4 + 16;            // bytes; +16 keeps lanes on distinct banks
 constexpr int RAW_BYTES = ((MAXR + 1) * RAW_STRIDE + 127) / 128 * 128;  // + one all-zero row for idle lanes
 constexpr int BIMG_BYTES = (TL / 4) * (MAXR / 8) * 128;   // one hi or lo image of a tile
@@ -50,23 +61,29 @@ constexpr int SMEM_BYTES = OFF_BIMG + 4 * BIMG_BYTES;
 static_assert(OFF_BIMG % 128 == 0, "operand images must be 128-byte aligned");
 
 // barrier indices
-enum { RAW_FULL = 0, RAW_EMPTY = 2, B_FULL = 4, B_EMPTY = 6, A_FULL = 8, A_EMPTY = 12, D_FULL = 16, D_EMPTY = 20, NBAR = 24 };
+enum {
+  RAW_FULL = 0, RAW_EMPTY = 2, B_FULL = 4, B_EMPTY = 6,
+  A_FULL = 8, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NTEAMS,
+  NBAR = D_EMPTY + NTEAMS
+};
+static_assert(NBAR * 8 + 8 <= OFF_RAW, "barrier area");
 
 // bounded wait: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void tc_wait(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok = 0;
-  for (uint32_t it = 0; it < (1u << 27); ++it) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     if (ok) return;
   }
   __trap();
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -76,7 +93,7 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 // K-major, no swizzle: LBO = byte step between the two 16-byte K chunks of one MMA, SBO = byte
-// step between 8-row groups (include/..., cute mma_sm100_desc.hpp SmemDescriptor bit layout)
+// step between 8-row groups (bit layout as in CUTLASS cute/arch/mma_sm100_desc.hpp)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
@@ -90,44 +107,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t b, 
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
+template <int ACC>
+__device__ __forceinline__ void mma_tf32_ts2(uint32_t d, uint32_t a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile("{\n.reg .b64 bd;\nmov.b64 bd, {%2, %3};\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, %5;\n}\n" ::"r"(d), "r"(a), "r"(desc_lo), "r"(desc_hi),
+               "r"(idesc), "n"(ACC)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-struct Params {
-  const float* const* rowptr;
-  int nrows;        // R <= 40
-  int ncols;        // N = R rounded up to 8
-  int64_t ntiles;   // ncells / TL
-  int nu0, nu1;     // units of team 0 / team 1
-  int ucol0[2 * UPT];        // [team * UPT + j]: first D column the unit needs (multiple of 8)
-  int uncol[2 * UPT];        //                   number of columns (multiple of 8, <= CAP[j])
-  const uint32_t* slot_tab;  // [team * UPT + j][4][32]: ra | rb << 8 | resident << 16  (row R = zero row)
-  double* partial;           // [cta][CAPSUM][256]
-  int64_t partial_stride;
-  int flush_chunks;
-};
-
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr),
-               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
                : "memory");
 }
 // issue a TMEM load of 8 columns as four float2 (no wait)
@@ -142,148 +131,140 @@ __device__ __forceinline__ void tmem_ld8v(uint32_t addr, float2 (&v)[4]) {
 __device__ __forceinline__ void pin8(float2 (&v)[4]) {
   asm volatile("" : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x), "+f"(v[3].y));
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// not volatile: the compiler may hoist and batch these loads
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-// Generator + drain team member.  team is 0 or 1, q = warp % 4 is the TMEM lane quarter.
-__device__ __forceinline__ void team_loop(const Params& p, const unsigned char* smem, uint64_t* bars, uint32_t tbase,
+struct Params {
+  const float* const* rowptr;
+  int nrows;        // R <= 40
+  int ncols;        // N = R rounded up to 8
+  int64_t ntiles;   // ncells / TL
+  int nu[NTEAMS];             // units per team
+  int ucol0[NTEAMS * UPT];    // [team * UPT + j]: first D column the unit needs (multiple of 8)
+  int uncol[NTEAMS * UPT];    //                   number of columns (multiple of 8, <= cap(j))
+  const uint32_t* slot_tab;   // [team * UPT + j][4][32]: ra | rb << 8  (row index R = zero row)
+  double* partial;            // [cta][CAPSUM][NTEAMTHREADS]
+  int64_t partial_stride;
+  int flush_chunks;
+  long long* prof;            // PROF only: [team warp q=0: 8 counters per team][mma: 8 counters]
+};
+
+// Generator + drain team member; q = warp % 4 is the TMEM lane quarter.
+__device__ __forceinline__ void team_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase,
                                           int team, int q, int lane) {
-  const int my_nu = team ? p.nu1 : p.nu0;
+  const int my_nu = p.nu[team];
   const int R = p.nrows;
   uint32_t rb_off[UPT], ra_off[UPT];
-  bool resident[UPT];
+  int ncol[UPT];
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
     uint32_t e = (uint32_t)R | ((uint32_t)R << 8);
     if (j < my_nu) e = p.slot_tab[((team * UPT + j) * 4 + q) * 32 + lane];
     ra_off[j] = (e & 0xFFu) * RAW_STRIDE;
     rb_off[j] = ((e >> 8) & 0xFFu) * RAW_STRIDE;
-    resident[j] = USE_OWN && ((e >> 16) & 1u);   // warp-uniform by construction
+    ncol[j] = p.uncol[team * UPT + j];
   }
-  const uint32_t own_off = (uint32_t)(lane < R ? lane : R) * RAW_STRIDE;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-  float2 acc0[cap(0) / 2], acc1[cap(1) / 2], acc2_[cap(2) / 2], acc3[cap(3) / 2];
+  const uint32_t d_tmem = tbase + lane_sel + TM_D + (uint32_t)team * MAXR;
+  const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
+  const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
+  const uint32_t bar_dfull = bars + (D_FULL + team) * 8, bar_dempty = bars + (D_EMPTY + team) * 8;
+  float2 acc0[cap(0) / 2], acc1[cap(1) / 2], acc2[cap(2) / 2];
 #pragma unroll
   for (int c = 0; c < cap(0) / 2; ++c) acc0[c] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < cap(1) / 2; ++c) acc1[c] = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < cap(2) / 2; ++c) acc2_[c] = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < cap(3) / 2; ++c) acc3[c] = make_float2(0.f, 0.f);
-  int ncol[UPT];
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) ncol[j] = p.uncol[team * UPT + j];
+  for (int c = 0; c < cap(2) / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
 
   uint32_t n_gen = 0;     // units generated by this team so far
   uint32_t n_drain = 0;   // units drained so far
   int since_flush = 0;
   double* my_partial = p.partial + (int64_t)blockIdx.x * p.partial_stride + team * 128 + q * 32 + lane;
 
+  long long t_raw = 0, t_gen = 0, t_aempty = 0, t_st = 0, t_dfull = 0, t_drain = 0, t_mark = 0;
+  auto tick = [&](long long& acc_t) {
+    if constexpr (PROF) { const long long now = clock64(); acc_t += now - t_mark; t_mark = now; }
+  };
   auto drain_into = [&](auto jj, auto& acc) {
     constexpr int J = decltype(jj)::value;
-    const uint32_t dbuf = (uint32_t)team * 2u + (n_drain & 1u);
-    const uint32_t d_tmem = tbase + lane_sel + dbuf * 64u;
-    tc_wait(&bars[D_FULL + dbuf], (n_drain >> 1) & 1u);
+    tc_wait(bar_dfull, n_drain & 1u);
     tc_fence_after();
-    float2 v[cap(J) / 8][4];
+    tick(t_dfull);
+    // two groups of 8 columns in flight at a time (register budget)
 #pragma unroll
-    for (int g = 0; g < cap(J) / 8; ++g)
-      if (g * 8 < ncol[J]) tmem_ld8v(d_tmem + g * 8, v[g]);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int g0 = 0; g0 < cap(J) / 8; g0 += 2) {
+      if (g0 * 8 < ncol[J]) {
+        float2 v[2][4];
 #pragma unroll
-    for (int g = 0; g < cap(J) / 8; ++g)
-      if (g * 8 < ncol[J]) pin8(v[g]);
+        for (int g = 0; g < 2; ++g)
+          if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol[J]) tmem_ld8v(d_tmem + (g0 + g) * 8, v[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol[J]) {
+            pin8(v[g]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[(g0 + g) * 4 + c] = __fadd2_rn(acc[(g0 + g) * 4 + c], v[g][c]);
+          }
+      }
+    }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[D_EMPTY + dbuf]);
-#pragma unroll
-    for (int g = 0; g < cap(J) / 8; ++g)
-      if (g * 8 < ncol[J]) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[g * 4 + c] = __fadd2_rn(acc[g * 4 + c], v[g][c]);
-      }
+    if (lane == 0) mbar_arrive(bar_dempty);
     ++n_drain;
+    tick(t_drain);
   };
   auto drain_dyn = [&](int j) {   // statically indexed accumulators behind a warp-uniform switch
     if (j == 0) drain_into(std::integral_constant<int, 0>{}, acc0);
     else if (j == 1) drain_into(std::integral_constant<int, 1>{}, acc1);
-    else if (j == 2) drain_into(std::integral_constant<int, 2>{}, acc2_);
-    else drain_into(std::integral_constant<int, 3>{}, acc3);
+    else drain_into(std::integral_constant<int, 2>{}, acc2);
+  };
+  auto flush_arr = [&](auto jj, auto& acc) {
+    constexpr int J = decltype(jj)::value;
+#pragma unroll
+    for (int c = 0; c < cap(J) / 2; ++c)
+      if (2 * c < ncol[J]) {
+        atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c) * NTEAMTHREADS, (double)acc[c].x);
+        atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c + 1) * NTEAMTHREADS, (double)acc[c].y);
+        acc[c] = make_float2(0.f, 0.f);
+      }
   };
   auto flush = [&]() {
-#pragma unroll
-    for (int c = 0; c < cap(0) / 2; ++c)
-      if (2 * c < ncol[0]) {
-        atomicAdd(my_partial + (int64_t)(capoff(0) + 2 * c) * 256, (double)acc0[c].x);
-        atomicAdd(my_partial + (int64_t)(capoff(0) + 2 * c + 1) * 256, (double)acc0[c].y);
-        acc0[c] = make_float2(0.f, 0.f);
-      }
-#pragma unroll
-    for (int c = 0; c < cap(1) / 2; ++c)
-      if (2 * c < ncol[1]) {
-        atomicAdd(my_partial + (int64_t)(capoff(1) + 2 * c) * 256, (double)acc1[c].x);
-        atomicAdd(my_partial + (int64_t)(capoff(1) + 2 * c + 1) * 256, (double)acc1[c].y);
-        acc1[c] = make_float2(0.f, 0.f);
-      }
-#pragma unroll
-    for (int c = 0; c < cap(2) / 2; ++c)
-      if (2 * c < ncol[2]) {
-        atomicAdd(my_partial + (int64_t)(capoff(2) + 2 * c) * 256, (double)acc2_[c].x);
-        atomicAdd(my_partial + (int64_t)(capoff(2) + 2 * c + 1) * 256, (double)acc2_[c].y);
-        acc2_[c] = make_float2(0.f, 0.f);
-      }
-#pragma unroll
-    for (int c = 0; c < cap(3) / 2; ++c)
-      if (2 * c < ncol[3]) {
-        atomicAdd(my_partial + (int64_t)(capoff(3) + 2 * c) * 256, (double)acc3[c].x);
-        atomicAdd(my_partial + (int64_t)(capoff(3) + 2 * c + 1) * 256, (double)acc3[c].y);
-        acc3[c] = make_float2(0.f, 0.f);
-      }
+    flush_arr(std::integral_constant<int, 0>{}, acc0);
+    flush_arr(std::integral_constant<int, 1>{}, acc1);
+    flush_arr(std::integral_constant<int, 2>{}, acc2);
   };
 
+  if constexpr (PROF) t_mark = clock64();
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    tc_wait(&bars[RAW_FULL + buf], (uint32_t)(it >> 1) & 1u);
-    const unsigned char* raw = smem + OFF_RAW + buf * RAW_BYTES;
+    tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
+    tick(t_raw);
+    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * RAW_BYTES);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
-      const unsigned char* cbase = raw + c * (CH * 4);
-      float2 own[CH / 2];
-      if constexpr (USE_OWN) {
-#pragma unroll
-        for (int v4 = 0; v4 < CH / 4; ++v4) {
-          const float4 t = *reinterpret_cast<const float4*>(cbase + own_off + v4 * 16);
-          own[v4 * 2] = make_float2(t.x, t.y);
-          own[v4 * 2 + 1] = make_float2(t.z, t.w);
-        }
-      }
+      const uint32_t cbase = raw + c * (CH * 4);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j < my_nu) {
-          const uint32_t abuf = (uint32_t)team * 2u + (n_gen & 1u);
-          const uint32_t a_tmem = tbase + lane_sel + 256u + abuf * 64u;
+          const uint32_t ab = n_gen & 1u;
+          const uint32_t a_tmem = a_tmem0 + ab * 64u;
           bool waited = false;
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            // 8 cells: partner row from shared memory, own row from registers (resident slots)
-            float2 pb[4], pa[4];
-#pragma unroll
-            for (int v4 = 0; v4 < 2; ++v4) {
-              const float4 t = *reinterpret_cast<const float4*>(cbase + rb_off[j] + h * 32 + v4 * 16);
-              pb[v4 * 2] = make_float2(t.x, t.y);
-              pb[v4 * 2 + 1] = make_float2(t.z, t.w);
-            }
-            if (USE_OWN && resident[j]) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pa[i] = own[h * 4 + i];
-            } else {
-#pragma unroll
-              for (int v4 = 0; v4 < 2; ++v4) {
-                const float4 t = *reinterpret_cast<const float4*>(cbase + ra_off[j] + h * 32 + v4 * 16);
-                pa[v4 * 2] = make_float2(t.x, t.y);
-                pa[v4 * 2 + 1] = make_float2(t.z, t.w);
-              }
-            }
+          for (int h = 0; h < 4; ++h) {   // 8 cells at a time
+            const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
+            const float4 a0 = lds128(cbase + ra_off[j] + h * 32), a1 = lds128(cbase + ra_off[j] + h * 32 + 16);
+            const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+            const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -295,18 +276,22 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
               lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);
             }
             if (!waited) {
-              tc_wait(&bars[A_EMPTY + abuf], ((n_gen >> 1) & 1u) ^ 1u);
+              tick(t_gen);
+              tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
               tc_fence_after();
               waited = true;
+              tick(t_aempty);
             }
             tmem_st8(a_tmem + h * 8, hi);
             tmem_st8(a_tmem + 32 + h * 8, lo);
           }
+          tick(t_gen);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[A_FULL + abuf]);
+          if (lane == 0) mbar_arrive(bar_afull + ab * 8);
           ++n_gen;
+          tick(t_st);
           // drain the unit generated before this one (its MMAs overlap this generation)
           if (n_gen > 1) drain_dyn(j > 0 ? j - 1 : my_nu - 1);
         }
@@ -317,31 +302,41 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[RAW_EMPTY + buf]);
+    if (lane == 0) mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
   }
   if (n_gen > 0) drain_dyn(my_nu - 1);
   flush();
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
+      long long* o = p.prof + team * 8;
+      o[0] = t_raw; o[1] = t_gen; o[2] = t_aempty; o[3] = t_st; o[4] = t_dfull; o[5] = t_drain; o[6] = n_gen;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
+  const uint32_t bars = smem_u32(bar_ptr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = p.nrows, N = p.ncols;
+  constexpr int W_TMA = NTEAMS * 4, W_MMA = W_TMA + 1;
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars[RAW_FULL + b], 1);
-      mbar_init(&bars[RAW_EMPTY + b], 10);
-      mbar_init(&bars[B_FULL + b], 2);
-      mbar_init(&bars[B_EMPTY + b], 1);
+      mbar_init(&bar_ptr[RAW_FULL + b], 1);
+      mbar_init(&bar_ptr[RAW_EMPTY + b], NTEAMS * 4 + 2);
+      mbar_init(&bar_ptr[B_FULL + b], 2);
+      mbar_init(&bar_ptr[B_EMPTY + b], 1);
     }
-    for (int b = 0; b < 4; ++b) {
-      mbar_init(&bars[D_FULL + b], 1);
-      mbar_init(&bars[D_EMPTY + b], 4);
-      mbar_init(&bars[A_FULL + b], 4);
-      mbar_init(&bars[A_EMPTY + b], 1);
+    for (int b = 0; b < 2 * NTEAMS; ++b) {
+      mbar_init(&bar_ptr[A_FULL + b], 4);
+      mbar_init(&bar_ptr[A_EMPTY + b], 1);
+    }
+    for (int b = 0; b < NTEAMS; ++b) {
+      mbar_init(&bar_ptr[D_FULL + b], 1);
+      mbar_init(&bar_ptr[D_EMPTY + b], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -351,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
     reinterpret_cast<uint32_t*>(smem + OFF_RAW + RAW_BYTES + R * RAW_STRIDE)[i] = 0u;
   }
   for (int i = tid; i < 4 * BIMG_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem + OFF_BIMG)[i] = 0u;
-  if (warp == 9) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -361,76 +356,103 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  if (warp < NTEAMS * 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_TEAM));
     team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+    if (warp == W_TMA) {
       // ---- TMA producer
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        tc_wait(&bars[RAW_EMPTY + buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        if (lane == 0) mbar_expect_tx(&bars[RAW_FULL + buf], (uint32_t)(R * TL * 4));
+        tc_wait(bars + (RAW_EMPTY + buf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        if (lane == 0) mbar_expect_tx(&bar_ptr[RAW_FULL + buf], (uint32_t)(R * TL * 4));
         __syncwarp();
         unsigned char* dst = smem + OFF_RAW + buf * RAW_BYTES;
         for (int r = lane; r < R; r += 32)
-          bulk_g2s(dst + r * RAW_STRIDE, p.rowptr[r] + tile * TL, TL * 4, &bars[RAW_FULL + buf]);
+          bulk_g2s(dst + r * RAW_STRIDE, p.rowptr[r] + tile * TL, TL * 4, &bar_ptr[RAW_FULL + buf]);
       }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
       // ---- MMA issuer
       const uint32_t leader = elect_one();
       const uint32_t lbo = (uint32_t)(N / 8) * 128u;     // next 4-cell group of the image
-      uint32_t n_unit[2] = {0u, 0u};
+      uint32_t n_unit[NTEAMS];
+      uint32_t idesc[NTEAMS * UPT], coff[NTEAMS * UPT];
+#pragma unroll
+      for (int t = 0; t < NTEAMS; ++t) n_unit[t] = 0u;
+#pragma unroll
+      for (int i = 0; i < NTEAMS * UPT; ++i) {
+        idesc[i] = make_idesc_tf32(p.uncol[i]);
+        coff[i] = (uint32_t)p.ucol0[i];                  // first column, = 16-byte units into an image group
+      }
+      long long m_afull = 0, m_dempty = 0, m_issue = 0, m_bfull = 0, m_mark = 0, m_start = 0;
+      if constexpr (PROF) m_start = clock64();
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        tc_wait(&bars[B_FULL + buf], (uint32_t)(it >> 1) & 1u);
+        if constexpr (PROF) m_mark = clock64();
+        tc_wait(bars + (B_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
+        if constexpr (PROF) m_bfull += clock64() - m_mark;
         const uint32_t img_hi = smem_u32(smem + OFF_BIMG + (buf * 2 + 0) * BIMG_BYTES);
         const uint32_t img_lo = smem_u32(smem + OFF_BIMG + (buf * 2 + 1) * BIMG_BYTES);
+        // descriptor of (image, 4-cell group g, first column col0): base + g * N + col0 in 16-byte units
+        const uint32_t dh_lo = (uint32_t)make_desc(img_hi, lbo, 128u), dl_lo = (uint32_t)make_desc(img_lo, lbo, 128u);
+        const uint32_t d_hi32 = (uint32_t)(make_desc(img_hi, lbo, 128u) >> 32);
+#pragma unroll
         for (int c = 0; c < NCH; ++c) {
+#pragma unroll
           for (int j = 0; j < UPT; ++j) {
-            for (int team = 0; team < 2; ++team) {
-              if (j >= (team ? p.nu1 : p.nu0)) continue;
+#pragma unroll
+            for (int team = 0; team < NTEAMS; ++team) {
+              if (j >= p.nu[team]) continue;
               const uint32_t n = n_unit[team]++;
-              const uint32_t abuf = (uint32_t)team * 2u + (n & 1u);
-              tc_wait(&bars[A_FULL + abuf], (n >> 1) & 1u);
-              tc_wait(&bars[D_EMPTY + abuf], ((n >> 1) & 1u) ^ 1u);
+              const uint32_t ab = n & 1u;
+              if constexpr (PROF) m_mark = clock64();
+              tc_wait(bars + (A_FULL + team * 2 + ab) * 8, (n >> 1) & 1u);
+              if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
+              tc_wait(bars + (D_EMPTY + team) * 8, (n & 1u) ^ 1u);
               tc_fence_after();
+              if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
+              const uint32_t d = tbase + TM_D + (uint32_t)team * MAXR;
+              const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
+              const uint32_t id = idesc[team * UPT + j];
+              const uint32_t o0 = coff[team * UPT + j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
               if (leader) {
-                const uint32_t idesc = make_idesc_tf32(p.uncol[team * UPT + j]);
-                const uint32_t coff = (uint32_t)(p.ucol0[team * UPT + j] / 8) * 128u;   // first 8-row group
-                const uint32_t d = tbase + abuf * 64u;          // D and A buffers share the index
-                const uint32_t a = tbase + 256u + abuf * 64u;
 #pragma unroll
                 for (int ks = 0; ks < CH / 8; ++ks) {
-                  const uint32_t goff = (uint32_t)(c * (CH / 4) + ks * 2) * lbo + coff;
-                  const uint64_t bh = make_desc(img_hi + goff, lbo, 128u);
-                  const uint64_t bl = make_desc(img_lo + goff, lbo, 128u);
-                  mma_tf32_ts(d, a + 32 + ks * 8, bh, idesc, ks > 0);   // P_lo * C_hi
-                  mma_tf32_ts(d, a + ks * 8, bl, idesc, 1);             // P_hi * C_lo
-                  mma_tf32_ts(d, a + ks * 8, bh, idesc, 1);             // P_hi * C_hi
+                  const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
+                  if (ks == 0) mma_tf32_ts2<0>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);   // P_lo * C_hi
+                  else mma_tf32_ts2<1>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);
+                  mma_tf32_ts2<1>(d, a + ks * 8, dl_lo + o, d_hi32, id);                       // P_hi * C_lo
+                  mma_tf32_ts2<1>(d, a + ks * 8, dh_lo + o, d_hi32, id);                       // P_hi * C_hi
                 }
-                tc_commit(&bars[A_EMPTY + abuf]);
-                tc_commit(&bars[D_FULL + abuf]);
+                tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
+                tc_commit(bars + (D_FULL + team) * 8);
               }
               __syncwarp();
+              if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
             }
           }
         }
-        if (leader) tc_commit(&bars[B_EMPTY + buf]);
+        if (leader) tc_commit(bars + (B_EMPTY + buf) * 8);
         __syncwarp();
+      }
+      if constexpr (PROF) {
+        if (blockIdx.x == 0 && lane == 0 && p.prof) {
+          long long* o = p.prof + NTEAMS * 8;
+          o[0] = m_afull; o[1] = m_dempty; o[2] = m_issue; o[3] = m_bfull; o[4] = clock64() - m_start;
+        }
       }
     } else {
       // ---- operand-image converters (64 threads): raw fp32 -> tf32 hi (round to nearest) + lo
-      const int ct = tid - 320;
+      const int ct = tid - (W_MMA + 1) * 32;
       const uint32_t ngrp = (uint32_t)(N / 8) * 128u;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        tc_wait(&bars[RAW_FULL + buf], (uint32_t)(it >> 1) & 1u);
-        tc_wait(&bars[B_EMPTY + buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
+        tc_wait(bars + (B_EMPTY + buf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
         const uint32_t raw = smem_u32(smem + OFF_RAW + buf * RAW_BYTES);
         const uint32_t img_hi = smem_u32(smem + OFF_BIMG + (buf * 2 + 0) * BIMG_BYTES);
         const uint32_t img_lo = smem_u32(smem + OFF_BIMG + (buf * 2 + 1) * BIMG_BYTES);
@@ -451,15 +473,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&bars[B_FULL + buf]);
-          mbar_arrive(&bars[RAW_EMPTY + buf]);
+          mbar_arrive(bars + (B_FULL + buf) * 8);
+          mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+  if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
 }
 
 }  // namespace tc

@@ -16,6 +16,7 @@ shell field, and all calls are collective.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass
 
@@ -181,6 +182,10 @@ class NativeBackend:
         self.info = nat.Info()
         nat.check(self.lib.bsk_plan_info(handle, C.byref(self.info)), "bsk_plan_info")
         self._cplans = {}
+        #: 0 = FP32-pipe tile kernel (default), 1 = tcgen05 tensor cores for eligible dense lists
+        #: (include/bskit_b200.h, bsk_cplan_set_path); BSKIT_B200_CONTRACTION=tensor selects 1
+        self.contraction_path = 1 if os.environ.get("BSKIT_B200_CONTRACTION", "") == "tensor" else 0
+        self.last_path = 0
 
     def close(self):
         if getattr(self, "handle", None):
@@ -268,6 +273,7 @@ class NativeBackend:
             self._cplans[key] = ent
         cp = ent[0]
         self._last_cplan = cp
+        nat.check(self.lib.bsk_cplan_set_path(cp, int(self.contraction_path)), "bsk_cplan_set_path")
         sums = torch.empty((njobs, len(rows)), dtype=torch.float64, device=self.device)
         ptrs = (C.c_void_p * nrows)(*row_ptrs)
         with torch.cuda.device(self.device):
@@ -276,6 +282,9 @@ class NativeBackend:
                                             C.cast(sums.data_ptr(), C.POINTER(C.c_double)),
                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                       "bsk_contract")
+        out = (C.c_int64 * 3)()
+        nat.check(self.lib.bsk_cplan_path(cp, out), "bsk_cplan_path")
+        self.last_path = int(out[2])
         return sums
 
     def reduce_list(self, fields, rows, ncells):
@@ -491,6 +500,8 @@ class Engine:
             sums = self.backend.reduce_list(fields, allrows, ncells).reshape(len(job_off), len(rows))
         else:
             sums = self.backend.contract(fields, rows, ncells, job_off)
+            if getattr(self.backend, "last_path", 0) == 1:
+                self.last_schedule = "tensor"
         _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)

@@ -148,6 +148,16 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
 int bsk_cplan_destroy(bsk_cplan* cp);
 int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, rounds, threads */
 
+/* Contraction path of a schedule.  path 0 (default): FP32-pipe tile kernel (packed FFMA2, exact
+ * round-to-nearest products).  path 1: tcgen05 tensor cores, 3xTF32 operands with the pair
+ * products written to TMEM, accumulators drained every 32 cells (relative error ~4e-7 instead of
+ * ~5e-8).  Path 1 is used only when the list is eligible: float32 fields and products, one job
+ * with zero offsets, at most 40 rows, at least 256 triangles, ncells a multiple of 128;
+ * otherwise bsk_contract runs path 0.  bsk_cplan_path: out = {tensor-core units of the
+ * schedule (0: not eligible), requested path, path the last bsk_contract call ran}. */
+int bsk_cplan_set_path(bsk_cplan* cp, int path);
+int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]);
+
 /* sums[j][t] = sum over local cells x of
  *     F[r1 + off[j][0]](x) * F[r2 + off[j][1]](x) * F[r3 + off[j][2]](x)
  * (replaces the per-triangle np.sum of main.py:1875, 2027-2055; the caller

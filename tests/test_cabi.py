@@ -34,6 +34,9 @@ def test_library_is_built_for_sm100a_with_tma_bulk_copies():
     assert "tile_contract_kernel" in sass
     assert "UBLKCP" in sass               # cp.async.bulk (TMA 1-D bulk copy) feeds the tile ring
     assert "SYNCS.ARRIVE.TRANS64" in sass  # mbarrier expect_tx
+    # the tensor-core contraction path: tcgen05.mma with the A operand in TMEM, tcgen05.st/ld
+    assert "tc_contract_kernel" in sass
+    assert "UTCHMMA" in sass and "STTM" in sass and "LDTM" in sass
 
 
 def test_argument_errors_are_reported_not_crashes():

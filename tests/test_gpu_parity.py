@@ -574,3 +574,47 @@ def test_downsample_mesh_and_npy_source(bk, syn, tmp_path):
     b_fine = bk.FFTBispectrum(src, kmin=kmin, kmax=kmax, dk=dk).measure_bispectrum_faster()["B"]
     b_coarse = bk.FFTBispectrum(got, kmin=kmin, kmax=kmax, dk=dk).measure_bispectrum_faster()["B"]
     assert_b_close(b_coarse, b_fine, 1e-9, 1e-11)
+
+
+def test_tensor_core_contraction_path(bk, syn):
+    """The tcgen05 (3xTF32, pair products in TMEM) contraction path agrees with a float64
+    reduction and with the FP32-pipe tile kernel on a dense list; ineligible calls (short
+    lists, float64 fields) fall back to the tile kernel."""
+    import torch
+    from bskit_b200 import engine as eng, _native as nat
+    dev = torch.device("cuda", 0)
+    g = eng.choose_grid(64, syn.BOX, 8.5 * syn.KF, "full")
+    e = eng.Engine(g, syn.BOX, nat.F32, device=dev)
+    assert e.ncells % 128 == 0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    nrows = 24
+    table = torch.randn((nrows, e.ncells), dtype=torch.float32, device=dev, generator=gen)
+    table += 0.3 * torch.sin(torch.arange(e.ncells, device=dev) * 1e-3)[None, :]   # non-zero skewness
+    t64 = table.double()
+    dense = np.array([[c, b, a] for a in range(nrows) for b in range(a, nrows) for c in range(b, nrows)
+                      if c <= a + b + 2])
+    assert len(dense) >= 256
+    want = np.array([(t64[a] * t64[b] * t64[c]).sum().item() for a, b, c in dense])
+    scale = np.abs(want).max()
+    tile = e.contract(table, dense)[0]
+    assert e.last_schedule == "tile"
+    e.backend.contraction_path = 1
+    tens = e.contract(table, dense)[0]
+    assert e.last_schedule == "tensor"
+    err_tile, err_tens = np.abs(tile - want).max() / scale, np.abs(tens - want).max() / scale
+    print(f"max err / max|sum|: tile {err_tile:.2e}, tensor {err_tens:.2e}")
+    assert err_tile < 2e-6, err_tile
+    assert err_tens < 5e-6, err_tens
+    assert_b_close(tens, want, rtol=RTOL_B, atol_rms=5e-6)
+    few = dense[:40]                                           # < 256 triangles: not eligible
+    got = e.contract(table, few)[0]
+    assert e.last_schedule in ("tile", "stream")
+    np.testing.assert_allclose(got, want[:40], rtol=1e-4, atol=5e-7 * scale)
+    e.close()
+    e64 = eng.Engine(g, syn.BOX, nat.F64, device=dev)
+    e64.backend.contraction_path = 1
+    got = e64.contract(t64.contiguous(), dense)[0]
+    assert e64.last_schedule == "tile"
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * scale)
+    e64.close()
