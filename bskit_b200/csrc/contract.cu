@@ -555,7 +555,7 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
   // widest units first, dealt alternately to the two teams; position j must fit cap(j)
   std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.ncol > y.ncol; });
   const int ncols = (R + 7) / 8 * 8;
-  std::vector<uint32_t> tab((size_t)NTEAMS * UPT * 128, idle);
+  std::vector<uint32_t> tab((size_t)NTEAMS * UPT * 128, idle | (1u << 16));
   for (int t = 0; t < NTEAMS; ++t) cp->tc_nu[t] = 0;
   std::unordered_map<int, int> slot_pos;   // slot id -> (team * UPT + j) * 4 + q
   for (int u = 0; u < nunits; ++u) {

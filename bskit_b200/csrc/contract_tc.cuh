@@ -41,6 +41,7 @@ constexpr int NTHREADS = NTEAMTHREADS + 128;
 #endif
 constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
 constexpr int REGS_TEAM = 144, REGS_AUX = 80;      // 384*144 + 128*80 = 512*128
+constexpr bool USE_OWN = false;   // lane v keeps row v of the chunk in registers across its team's units
 static_assert(NTEAMTHREADS * REGS_TEAM + 128 * REGS_AUX <= NTHREADS * (65536 / NTHREADS / 8 * 8), "register split");
 // D columns a unit may need, by position j in its team (units are dealt to the teams in order of
 // decreasing width): a pair (a <= b) only meets rows c >= b, so most units need few columns
@@ -163,14 +164,18 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
   const int R = p.nrows;
   uint32_t rb_off[UPT], ra_off[UPT];
   int ncol[UPT];
+  bool resident[UPT];   // warp-uniform: every lane's first row is row `lane` (or the lane is idle)
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
-    uint32_t e = (uint32_t)R | ((uint32_t)R << 8);
+    uint32_t e = (uint32_t)R | ((uint32_t)R << 8) | (1u << 16);
     if (j < my_nu) e = p.slot_tab[((team * UPT + j) * 4 + q) * 32 + lane];
     ra_off[j] = (e & 0xFFu) * RAW_STRIDE;
     rb_off[j] = ((e >> 8) & 0xFFu) * RAW_STRIDE;
+    resident[j] = USE_OWN && __all_sync(0xffffffffu, (e >> 16) & 1u);
+    // idle lanes of a resident slot multiply their own row by the zero row
     ncol[j] = p.uncol[team * UPT + j];
   }
+  const uint32_t own_off = (uint32_t)(lane < R ? lane : R) * RAW_STRIDE;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint32_t d_tmem = tbase + lane_sel + TM_D + (uint32_t)team * MAXR;
   const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
@@ -253,6 +258,11 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       const uint32_t cbase = raw + c * (CH * 4);
+      float4 own[CH / 4];
+      if constexpr (USE_OWN) {
+#pragma unroll
+        for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + own_off + v4 * 16);
+      }
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j < my_nu) {
@@ -262,7 +272,14 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
 #pragma unroll
           for (int h = 0; h < 4; ++h) {   // 8 cells at a time
             const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
-            const float4 a0 = lds128(cbase + ra_off[j] + h * 32), a1 = lds128(cbase + ra_off[j] + h * 32 + 16);
+            float4 a0, a1;
+            if (USE_OWN && resident[j]) {
+              a0 = own[2 * h];
+              a1 = own[2 * h + 1];
+            } else {
+              a0 = lds128(cbase + ra_off[j] + h * 32);
+              a1 = lds128(cbase + ra_off[j] + h * 32 + 16);
+            }
             const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
             const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
             uint32_t hi[8], lo[8];
