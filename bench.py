@@ -225,10 +225,12 @@ def main():
         del tmp
     accum = nat.F32 if args.accum == "f32" else nat.F64
 
-    def make(policy):
+    def make(policy, tensor=False):
         g = eng.choose_grid(nmesh, syn.BOX, edges[:, 1].max(), policy, world)
         gn = eng.choose_grid(nmesh, syn.BOX, edges[:, 1].max(), "auto", world)
         e_data = eng.Engine(g, syn.BOX, nat.F32, device=dev, accum_precision=accum)
+        if tensor:
+            e_data.backend.contraction_path = 1     # tcgen05 path (include/bskit_b200.h, bsk_cplan_set_path)
         e_norm = eng.Engine(gn, syn.BOX, nat.F64, device=dev)
         return e_data, e_norm
 
@@ -244,8 +246,8 @@ def main():
         eng._mark(marks, "norm_done", e_data)
         return b, ntri_v, kmean
 
-    def timed(policy, steps, warmup, with_clocks=False):
-        e_data, e_norm = make(policy)
+    def timed(policy, steps, warmup, with_clocks=False, tensor=False):
+        e_data, e_norm = make(policy, tensor)
         slab = e_data.local_slab(host)
         for _ in range(warmup):
             out = step(e_data, e_norm, slab)
@@ -287,7 +289,7 @@ def main():
         stages = {k: float(np.mean(v)) for k, v in stages.items()}
         info = e_data.backend.cplan_info()
         res = dict(ms_per_step=ms / steps, stages_ms=stages, launches=launches, out=out,
-                   grid=e_data.grid, ncells=e_data.ncells, cplan=info,
+                   grid=e_data.grid, ncells=e_data.ncells, cplan=info, schedule=e_data.last_schedule,
                    clocks=sampler.summary() if sampler else None)
         e_data.close()
         e_norm.close()
@@ -302,6 +304,8 @@ def main():
                               "stages_ms": full["stages_ms"], "gpu_launches": full["launches"]}))
         return
     auto = timed("auto", args.steps, args.warmup)
+    # the same step with the contraction on the tensor cores (opt-in path, reported beside the default)
+    tens = timed("full", 2, 1, tensor=True) if accum == nat.F32 else None
 
     # ---- e2e: the user-facing API from (pinned) host memory, result back on the host
     def e2e_once():
@@ -404,6 +408,21 @@ def main():
                       "note": "exact band-limited evaluation (library default); same outputs"},
         "checks": {"api_vs_engine_max_abs_over_rms": api_agree},
     }
+    if tens is not None:
+        t_tc = tens["stages_ms"]["contract"] * 1e-3
+        # issued: 3 MMAs (P_lo*C_hi, P_hi*C_lo, P_hi*C_hi) of 2*128*N flops per cell and unit;
+        # sum of N over the units of the S=40 all-triangle schedule = 184
+        issued_tc = 6.0 * 128.0 * 184.0 * cells if (len(edges) == 40 and ntri == 6730) else None
+        line["tensor_path"] = {
+            "kernel": "tc_contract_kernel (tcgen05.mma kind::tf32, 3xTF32, A operand in TMEM)",
+            "schedule": tens["schedule"], "ms_per_step": tens["ms_per_step"],
+            "contract_ms": t_tc * 1e3, "fp32_pipe_contract_ms": t_contract * 1e3,
+            "max_abs_diff_vs_fp32_pipe_over_rms": float(np.max(np.abs(tens["out"][0] - bf)) / rms),
+            "roofline": {"bound": "tensor", "achieved": (issued_tc / t_tc / 1e12) if issued_tc else None,
+                         "peak": 741.0, "unit": "TFLOP/s",
+                         "frac": (issued_tc / t_tc / 1e12 / 741.0) if issued_tc else None,
+                         "peak_source": "measured TF32 cuBLAS 8192^3 on this pool's B200 (profiles/r1_extra_peaks.txt)"},
+            "note": "opt-in (BSKIT_B200_CONTRACTION=tensor): bounded by operand generation, see DESIGN.md"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
