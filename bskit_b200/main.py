@@ -47,7 +47,8 @@ __all__ = [
     "number_field", "k_field", "pk_FFT", "compute_Nbin", "compute_k_means_on_grid",
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
     "combine_gridinfo_and_unnormalized", "clear_cache",
-    "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "downsample_mesh",
+    "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "measure_subboxes",
+    "downsample_mesh",
 ]
 
 F32, F64 = 0, 1
@@ -412,6 +413,45 @@ def field_subbox_pm(box_multiindex, nsub_per_side, source):
     sub = mesh.array[i0[0]:i0[0] + ns, i0[1]:i0[1] + ns, i0[2]:i0[2] + ns]
     sub = np.ascontiguousarray(sub) if isinstance(sub, np.ndarray) else sub.contiguous()
     return ArrayMesh(sub, mesh.attrs["BoxSize"] / float(nsub_per_side), compensation=mesh.compensation)
+
+
+def measure_subboxes(source, nsub_per_side, start_subbox_ind=0, end_subbox_ind=None,
+                     meas_type="unnorm_b_value", out_file_prefix=None, imin=0, imax=10 ** 9,
+                     second=None, third=None, **fftb_kwargs):
+    """Per-sub-box measurements, the loop of ``scripts/measure/measure_subbox_bs_fast.py:246-295``:
+    for every sub-box index in [start_subbox_ind, end_subbox_ind] cut the (Nmesh/nsub)^3 sub-cube
+    of each input mesh (:func:`field_subbox_pm`), build an :class:`FFTBispectrum` with
+    ``Nmesh/nsub`` and ``BoxSize/nsub`` -- the k bins stay in the units passed in, as in the
+    reference -- and run ``measure_gridinfo_faster`` (``meas_type='grid_info'``) or
+    ``measure_bispectrum_faster`` (``'unnorm_b_value'``).  With ``out_file_prefix`` every sub-box
+    writes ``<prefix>_subbox<ind>.dat`` in the reference's format.  ``fftb_kwargs`` are the
+    binning / triangle keywords of the constructor.  Returns ``{ind: result dict}``."""
+    if meas_type not in ("grid_info", "unnorm_b_value"):
+        raise ValueError("meas_type must be 'grid_info' or 'unnorm_b_value'")
+    if third is not None and second is None:
+        raise ValueError("need second mesh if third mesh is input!")
+    meshes = [_as_mesh(m) for m in (source, second, third) if m is not None]
+    nsub = int(nsub_per_side)
+    if end_subbox_ind is None:
+        end_subbox_ind = nsub ** 3 - 1
+    if not (0 <= start_subbox_ind <= end_subbox_ind < nsub ** 3):
+        raise ValueError("sub-box indices must lie in [0, nsub_per_side^3)")
+    grid_only = meas_type == "grid_info"
+    results = {}
+    for ind in range(int(start_subbox_ind), int(end_subbox_ind) + 1):
+        multi = subbox_index_to_multiindex(ind, nsub)
+        subs = [field_subbox_pm(multi, nsub, m) for m in meshes] + [None, None]
+        fftb = FFTBispectrum(subs[0], second=subs[1], third=subs[2], for_grid_info_only=grid_only,
+                             **fftb_kwargs)
+        out_file = None if out_file_prefix is None else "%s_subbox%d.dat" % (out_file_prefix, ind)
+        try:
+            if grid_only:
+                results[ind] = fftb.measure_gridinfo_faster(imin=imin, imax=imax, out_file=out_file)
+            else:
+                results[ind] = fftb.measure_bispectrum_faster(imin=imin, imax=imax, out_file=out_file)
+        finally:
+            fftb.close()
+    return results
 
 
 def downsample_mesh(mesh, Nmesh_new, device=None):
