@@ -22,7 +22,7 @@ EXPORTS = (
     "bsk_set_compensation", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
     "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_cplan_set_path",
     "bsk_cplan_path", "bsk_contract",
-    "bsk_reduce_list", "bsk_launch_count",
+    "bsk_reduce_list", "bsk_paint_cic", "bsk_launch_count",
 )
 
 
@@ -76,6 +76,7 @@ def lib():
     L.bsk_cplan_path.argtypes = [vp, C.POINTER(C.c_int64)]
     L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     L.bsk_reduce_list.argtypes = [C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
+    L.bsk_paint_cic.argtypes = [vp, ip, C.c_int64, ip, dp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

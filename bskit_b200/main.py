@@ -48,7 +48,7 @@ __all__ = [
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
     "combine_gridinfo_and_unnormalized", "clear_cache",
     "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "measure_subboxes",
-    "downsample_mesh",
+    "downsample_mesh", "paint_cic",
 ]
 
 F32, F64 = 0, 1
@@ -452,6 +452,39 @@ def measure_subboxes(source, nsub_per_side, start_subbox_ind=0, end_subbox_ind=N
         finally:
             fftb.close()
     return results
+
+
+def paint_cic(positions, Nmesh, BoxSize, compensated=True, device=None):
+    """Paint particles onto an ``Nmesh``^3 mesh with the cloud-in-cell window on the GPU and
+    return the ``1 + delta`` field (mean 1) as an :class:`ArrayMesh` holding a float32 CUDA tensor
+    -- the particle-input step of the reference's drivers, ``catalog.to_mesh(Nmesh=..., BoxSize=...,
+    window='cic', compensated=True)`` (scripts/measure/measure_bs_fast.py:209-217).  With
+    ``compensated`` the CIC window compensation is queued and applied in the forward transform,
+    as nbodykit queues it.  ``positions``: (npart, 3) numpy array or torch tensor (float32/64),
+    wrapped periodically."""
+    import ctypes as C
+    import torch
+    from . import _native as nat
+    lib = nat.lib()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise nat.NativeError("bskit_b200 runs on CUDA devices only (no CPU fallback)")
+    pos = positions if torch.is_tensor(positions) else torch.from_numpy(np.ascontiguousarray(positions))
+    if pos.ndim != 2 or pos.shape[1] != 3:
+        raise ValueError("positions must have shape (npart, 3)")
+    if pos.dtype not in (torch.float32, torch.float64):
+        pos = pos.to(torch.float64)
+    pos = pos.to(dev).contiguous()
+    n = int(Nmesh)
+    box = np.ones(3) * np.asarray(BoxSize, dtype=np.float64)
+    mesh = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.bsk_paint_cic(C.c_void_p(pos.data_ptr()), nat.F32 if pos.dtype == torch.float32 else nat.F64,
+                                    int(pos.shape[0]), n, nat.dptr(box), C.c_void_p(mesh.data_ptr()),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "bsk_paint_cic")
+    if pos.shape[0] > 0:
+        mesh *= float(n) ** 3 / float(pos.shape[0])
+    return ArrayMesh(mesh, box, compensation=CompensateCIC(n) if compensated else None)
 
 
 def downsample_mesh(mesh, Nmesh_new, device=None):

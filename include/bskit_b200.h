@@ -182,6 +182,15 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
 int bsk_reduce_list(const void* const* row_ptrs, int nrows, int precision, int64_t ncells, int ntri,
                     const int32_t* rows, double* sums, void* cuda_stream);
 
+/* Cloud-in-cell mass assignment (the step before the path for particle inputs; replaces
+ * catalog.to_mesh(window='cic') + paint of scripts/measure/measure_bs_fast.py:209-217).
+ *   pos     device [npart][3] positions (float32 or float64 per `precision`), any real values:
+ *           they are wrapped periodically into the box
+ *   mesh    device out float32 [nmesh][nmesh][nmesh], zeroed by the call; holds the weight sums
+ *           (divide by npart / nmesh^3 for 1 + delta) */
+int bsk_paint_cic(const void* pos, int precision, int64_t npart, int nmesh, const double boxsize[3],
+                  float* mesh, void* cuda_stream);
+
 /* number of kernels this library has launched since load (bench bookkeeping) */
 int64_t bsk_launch_count(void);
 

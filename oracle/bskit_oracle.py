@@ -358,3 +358,26 @@ def brute_force_triangle(meshes, box, bins3):
     b = total.real * L.prod() ** 2
     with np.errstate(divide="ignore", invalid="ignore"):
         return b, count, ksum / count
+
+
+def paint_cic(pos, nmesh, boxsize):
+    """Cloud-in-cell mass assignment, float64 (test oracle for bsk_paint_cic; the reference gets
+    this from nbodykit's ``catalog.to_mesh(window='cic')``, scripts/measure/measure_bs_fast.py:
+    209-217).  Mesh points at integer multiples of BoxSize/Nmesh, weights prod (1 - |g - i|) on
+    the 8 surrounding points, periodic.  Returns the weight sums (N,N,N)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    box = np.ones(3) * np.asarray(boxsize, dtype=np.float64)
+    n = int(nmesh)
+    g = pos * (n / box)[None, :]
+    f = np.floor(g)
+    d = g - f
+    i0 = np.mod(f.astype(np.int64), n)
+    i1 = np.mod(i0 + 1, n)
+    mesh = np.zeros((n, n, n))
+    for ax in (0, 1):
+        for ay in (0, 1):
+            for az in (0, 1):
+                w = ((d[:, 0] if ax else 1 - d[:, 0]) * (d[:, 1] if ay else 1 - d[:, 1]) *
+                     (d[:, 2] if az else 1 - d[:, 2]))
+                np.add.at(mesh, ((i1 if ax else i0)[:, 0], (i1 if ay else i0)[:, 1], (i1 if az else i0)[:, 2]), w)
+    return mesh

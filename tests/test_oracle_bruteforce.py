@@ -66,3 +66,19 @@ def test_pk_fft_matches_direct_mode_average():
     assert abs(nb - sel.sum()) < 1e-8
     np.testing.assert_allclose(p, (np.abs(cube[sel]) ** 2).mean() * box ** 3, rtol=1e-11)
     np.testing.assert_allclose(km, kk[sel].mean(), rtol=1e-11)
+
+
+def test_oracle_cic_painting_properties():
+    """CIC oracle: a particle on a mesh point puts all its weight there, one at a
+    cell centre 1/8 on each corner, periodic wrap, and the total weight equals the particle count."""
+    from oracle import bskit_oracle as orc
+    n, box = 8, 16.0
+    m = orc.paint_cic(np.array([[4.0, 6.0, 2.0]]), n, box)
+    assert m[2, 3, 1] == 1.0 and m.sum() == 1.0
+    m = orc.paint_cic(np.array([[15.0, 15.0, 15.0]]), n, box)           # centre of the last cell: wraps
+    assert np.allclose(m[[7, 0]][:, [7, 0]][:, :, [7, 0]], 0.125) and np.isclose(m.sum(), 1.0)
+    m = orc.paint_cic(np.array([[-1.0, 17.0, 33.0]]), n, box)           # outside the box: periodic
+    assert np.isclose(m.sum(), 1.0) and np.isclose(m[7, 0, 0], 0.125)
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(0, box, size=(1000, 3))
+    assert np.isclose(orc.paint_cic(pos, n, box).sum(), 1000.0)
