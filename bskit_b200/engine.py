@@ -635,14 +635,26 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
         rows = pos[tri]
         job_off = np.asarray(job_seg_off, dtype=np.int64) * seg
         m = engine.grid.neval
-        if symmetric and engine.world == 1 and m % 2 == 0:
-            # Unit-amplitude and |k|-weighted shells are inversion symmetric, f(-x) = f(x), so
-            # x-planes ix and M-ix have equal sums: total = 2*sum(planes 0..M/2) - plane 0 - plane M/2.
-            plane, half = m * m, m // 2
-            part = lambda c0, c1: engine.contract([f[c0:c1] for f in fields], rows, job_off)  # noqa: E731
-            out[:, batch] = (2.0 * part(0, (half + 1) * plane) - part(0, plane)
-                             - part(half * plane, (half + 1) * plane))
+        if symmetric and engine.world == 1 and m % 2 == 0 and table.shape[1] == m ** 3:
+            # Unit-amplitude and |k|-weighted shells depend on |k| only, so they are even in every
+            # axis: f(x,y,z) = f(-x,y,z) = ...  The sum over the grid is the sum over the octant
+            # [0, M/2]^3 with multiplicity w = wx wy wz (w_axis = 1 on the planes 0 and M/2, else 2).
+            # Scaling every field by w^(1/3) puts the weight into the triple product, so one
+            # contraction over (M/2+1)^3 cells replaces the full-grid one (8x fewer cells).
+            h = m // 2 + 1
+            w1 = torch.full((h,), 2.0, dtype=torch.float64, device=table.device)
+            w1[0] = 1.0
+            w1[h - 1] = 1.0
+            w3 = (w1[:, None, None] * w1[None, :, None] * w1[None, None, :]) ** (1.0 / 3.0)
+            ncell_o = (h ** 3 + 3) // 4 * 4
+            octant = torch.zeros((table.shape[0], ncell_o), dtype=table.dtype, device=table.device)
+            octant[:, :h ** 3] = (table.view(-1, m, m, m)[:, :h, :h, :h] * w3.to(table.dtype)).reshape(table.shape[0], -1)
+            ofields = []
+            for sidx in range(nseg):
+                ofields += [octant[sidx * nb + r] for r in range(nb)] + [octant[sidx * nb]] * (seg - nb)
+            out[:, batch] = engine.contract(ofields, rows, job_off)
             _mark(marks, "contract_done", engine)
+            del octant, ofields
         else:
             out[:, batch] = engine.contract(fields, rows, job_off, marks=marks)
         del table, fields
