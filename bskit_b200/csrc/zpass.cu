@@ -150,14 +150,39 @@ zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
   __syncthreads();
   const int64_t groups_per_plane = M / RPC;
   const int64_t ngroups = planes * groups_per_plane;
+  // The kept coefficients of the NEXT row group are fetched into registers while the current
+  // group is transformed (the loads are the only long-latency operation of the loop); groups
+  // with more than NPRE elements per thread (bins up to Nyquist) load in place instead.
+  constexpr int NPRE = 4;
+  const bool prefetch = RPC * Kz <= NPRE * kZThreads;
+  double2 pre[NPRE];
+  auto fetch = [&](int64_t g) {
+    const int64_t pl = g / groups_per_plane;
+    const int yy = (int)(g - pl * groups_per_plane) * RPC;
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+      const int e = tid + q * kZThreads;
+      if (e < RPC * Kz) pre[q] = ycols[((int64_t)pl * Kz + e / RPC) * M + yy + e % RPC];
+    }
+  };
+  if (prefetch && (int64_t)blockIdx.x < ngroups) fetch(blockIdx.x);
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int64_t plane = grp / groups_per_plane;
     const int y0 = (int)(grp - plane * groups_per_plane) * RPC;
-    // ---- load the kept coefficients X[kz], kz < Kz (entries >= Kz are implicitly zero)
-    for (int e = tid; e < RPC * Kz; e += blockDim.x) {
-      const int r = e % RPC, kz = e / RPC;
-      const double2 g = ycols[((int64_t)plane * Kz + kz) * M + y0 + r];
-      sm[r * ROWLEN + padidx(kz)] = cplx{g.x, g.y};
+    // ---- the kept coefficients X[kz], kz < Kz (entries >= Kz are implicitly zero)
+    if (prefetch) {
+#pragma unroll
+      for (int q = 0; q < NPRE; ++q) {
+        const int e = tid + q * kZThreads;
+        if (e < RPC * Kz) sm[(e % RPC) * ROWLEN + padidx(e / RPC)] = cplx{pre[q].x, pre[q].y};
+      }
+      if (grp + gridDim.x < ngroups) fetch(grp + gridDim.x);
+    } else {
+      for (int e = tid; e < RPC * Kz; e += blockDim.x) {
+        const int r = e % RPC, kz = e / RPC;
+        const double2 g = ycols[((int64_t)plane * Kz + kz) * M + y0 + r];
+        sm[r * ROWLEN + padidx(kz)] = cplx{g.x, g.y};
+      }
     }
     __syncthreads();
     if (tid < NT) {
