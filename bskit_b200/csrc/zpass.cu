@@ -17,27 +17,26 @@ namespace bsk {
 using zfft::cplx;
 
 // [x][nsh][Kz][Ky] (after the x transform; ky contiguous) -> [nsh][mxl][Kz][M]  (y contiguous,
-// zero padded): contiguous reads and writes
-__global__ void scatter_y_kernel(const double2* __restrict__ xcols, double2* __restrict__ ycols,
-                                 int M, int Ky, int Kz, int nsh, int mx0, int mxl) {
+// zero padded): contiguous reads and writes.  One CTA per (shell, plane): no 64-bit divisions in
+// the element loop (M is a power of two on this path: log2m).
+__global__ void __launch_bounds__(256)
+scatter_y_kernel(const double2* __restrict__ xcols, double2* __restrict__ ycols,
+                 int M, int log2m, int Ky, int Kz, int nsh, int mx0, int mxl) {
   const int nc = (Ky - 1) / 2;
-  const int64_t total = (int64_t)nsh * mxl * Kz * M;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int iy = (int)(i % M);
-    int64_t r = i / M;
-    const int kz = (int)(r % Kz);
-    r /= Kz;
-    const int xl = (int)(r % mxl);
-    const int s = (int)(r / mxl);
+  const int xl = blockIdx.x % mxl, s = blockIdx.x / mxl;
+  const double2* __restrict__ src = xcols + ((int64_t)(mx0 + xl) * nsh + s) * Kz * Ky;
+  double2* __restrict__ dst = ycols + ((int64_t)s * mxl + xl) * Kz * M;
+  const int total = Kz * M;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int iy = i & (M - 1), kz = i >> log2m;
     int jy;
     if (Ky == M) jy = iy;
     else if (iy <= nc) jy = iy;
     else if (iy >= M - nc) jy = iy - M + Ky;
     else jy = -1;
     double2 v = make_double2(0.0, 0.0);
-    if (jy >= 0) v = xcols[(((int64_t)(mx0 + xl) * nsh + s) * Kz + kz) * Ky + jy];
-    ycols[i] = v;
+    if (jy >= 0) v = src[kz * Ky + jy];
+    dst[i] = v;
   }
 }
 
@@ -127,7 +126,7 @@ struct Stages {
 
 // M = 2H.  Rows are (plane, y); a CTA handles RPC consecutive y of one plane.
 template <int H, typename TS>
-__global__ void __launch_bounds__(kZThreads)
+__global__ void __launch_bounds__(kZThreads, 5)
 zpass_c2r_kernel(const double2* __restrict__ ycols,  // [planes][Kz][M]
                  TS* __restrict__ fields,            // [planes][M][M]
                  int Kz, int64_t planes, const double2* __restrict__ wtab) {
@@ -237,10 +236,9 @@ bool zpass_supported(int M) {
 // ycols scratch must hold nsh*mxl*Kz*M complex128; wtab = e^{2 pi i j/M}, j < M
 int zpass_run(int M, bool store_f32, const void* xcols, void* ycols, void* fields, int Ky, int Kz,
               int nsh, int mx0, int mxl, const double2* wtab, cufftHandle yplan, cudaStream_t st) {
-  const int64_t total = (int64_t)nsh * mxl * Kz * M;
-  int64_t g = (total + 255) / 256;
-  scatter_y_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(
-      (const double2*)xcols, (double2*)ycols, M, Ky, Kz, nsh, mx0, mxl);
+  int log2m = 0;
+  while ((1 << log2m) < M) ++log2m;
+  scatter_y_kernel<<<nsh * mxl, 256, 0, st>>>((const double2*)xcols, (double2*)ycols, M, log2m, Ky, Kz, nsh, mx0, mxl);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   BSK_FFT(cufftExecZ2Z(yplan, (cufftDoubleComplex*)ycols, (cufftDoubleComplex*)ycols, CUFFT_INVERSE));
