@@ -576,14 +576,14 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
     const size_t pi = (size_t)ta[t] * R + tb[t];
     const int pos = slot_pos[pair_slot[pi]], lane = pair_lane[pi];
     const int q = pos % 4, tj = pos / 4, team = tj / UPT, j = tj % UPT;
-    tri_slot[t] = (capoff(j) + tcc[t] - cp->tc_col0[tj]) * NTEAMTHREADS + team * 128 + q * 32 + lane;
+    tri_slot[t] = ((team * CAPSUM) + capoff(j) + tcc[t] - cp->tc_col0[tj]) * 128 + q * 32 + lane;
   }
   cp->tc_units = nunits; cp->tc_ncols = ncols;
   if (cudaMalloc((void**)&cp->d_tc_slots, sizeof(uint32_t) * tab.size()) != cudaSuccess) return false;
   cudaMemcpy(cp->d_tc_slots, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice);
   if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int) * (size_t)ntri) != cudaSuccess) return false;
   cudaMemcpy(cp->d_tc_tri_slot, tri_slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice);
-  const size_t stride = (size_t)CAPSUM * NTEAMTHREADS;
+  const size_t stride = (size_t)NTEAMS * CAPSUM * 128;
   if (cudaMalloc((void**)&cp->d_tc_partial, sizeof(double) * stride * cp->sm_count) != cudaSuccess) return false;
   return true;
 }
@@ -598,7 +598,7 @@ static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStr
   for (int t = 0; t < NTEAMS; ++t) p.nu[t] = cp->tc_nu[t];
   p.slot_tab = cp->d_tc_slots;
   p.partial = cp->d_tc_partial;
-  p.partial_stride = (int64_t)CAPSUM * NTEAMTHREADS;
+  p.partial_stride = (int64_t)CAPSUM * 128;            // per team; a CTA owns NTEAMS of them
   for (int i = 0; i < NTEAMS * UPT; ++i) { p.ucol0[i] = cp->tc_col0[i]; p.uncol[i] = cp->tc_ncol[i]; }
   p.flush_chunks = 512;
   p.prof = nullptr;
@@ -610,7 +610,7 @@ static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStr
 #endif
   const int ncta = (int)std::min<int64_t>(p.ntiles, cp->sm_count);
   BSK_CUDA(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0, sizeof(double) * (size_t)ncta * p.partial_stride, st));
+  BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0, sizeof(double) * (size_t)ncta * NTEAMS * p.partial_stride, st));
   tc_contract_kernel<<<ncta, NTHREADS, SMEM_BYTES, st>>>(p);
   count_launch();
   BSK_CUDA(cudaGetLastError());
@@ -619,15 +619,19 @@ static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStr
     long long h[64];
     cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
     for (int t = 0; t < NTEAMS; ++t)
-      fprintf(stderr, "tc prof team %d: units %lld | per unit: raw %.0f gen %.0f a_empty %.0f st+arrive %.0f d_full %.0f drain %.0f\n", t,
-              h[t * 8 + 6], (double)h[t * 8] / h[t * 8 + 6], (double)h[t * 8 + 1] / h[t * 8 + 6], (double)h[t * 8 + 2] / h[t * 8 + 6],
-              (double)h[t * 8 + 3] / h[t * 8 + 6], (double)h[t * 8 + 4] / h[t * 8 + 6], (double)h[t * 8 + 5] / h[t * 8 + 6]);
+      fprintf(stderr, "tc prof team %d: units %lld | per unit: raw %.0f gen %.0f a_empty %.0f st+arrive %.0f\n", t, h[t * 8 + 6],
+              (double)h[t * 8] / h[t * 8 + 6], (double)h[t * 8 + 1] / h[t * 8 + 6], (double)h[t * 8 + 2] / h[t * 8 + 6],
+              (double)h[t * 8 + 3] / h[t * 8 + 6]);
     const long long* m = h + NTEAMS * 8;
     fprintf(stderr, "tc prof mma: total %lld cycles: a_full %lld d_empty %lld issue %lld b_full %lld\n", m[4], m[0], m[1], m[2], m[3]);
+    for (int t = 0; t < NTEAMS; ++t) {
+      const long long* dr = h + (NTEAMS + 1 + t) * 8;
+      fprintf(stderr, "tc prof drain %d: units %lld | per unit: wait %.0f work %.0f\n", t, dr[2], (double)dr[0] / dr[2], (double)dr[1] / dr[2]);
+    }
   }
 #endif
   fold_partials_kernel<<<(int)std::min<int64_t>((cp->ntri + 127) / 128, 148 * 8), 128, 0, st>>>(
-      cp->d_tc_partial, p.partial_stride, ncta, 1, cp->ntri, 0, cp->d_tc_tri_slot, sums);
+      cp->d_tc_partial, (int64_t)NTEAMS * p.partial_stride, ncta, 1, cp->ntri, 0, cp->d_tc_tri_slot, sums);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   return BSK_OK;

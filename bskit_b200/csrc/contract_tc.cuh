@@ -31,32 +31,41 @@ namespace tc {
 constexpr int CH = 32;            // cells per chunk = K extent of one unit
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
+constexpr int WIN = 2;            // chunks accumulated in TMEM before a drain (divides NCH): the
+                                  // accumulator truncates, so the window bounds the bias (~3.5e-7 per chunk)
+static_assert(NCH % WIN == 0, "window");
 constexpr int MAXR = 40;          // rows (N <= 40)
-constexpr int NTEAMS = 3;
-constexpr int UPT = 3;            // units per team (NTEAMS * UPT * 128 pair rows at most)
+constexpr int NTEAMS = 2;
+constexpr int UPT = 4;            // units per team (NTEAMS * UPT * 128 pair rows at most)
 constexpr int NTEAMTHREADS = NTEAMS * 128;
-constexpr int NTHREADS = NTEAMTHREADS + 128;
+constexpr int NTHREADS = 2 * NTEAMTHREADS + 128;    // generator teams + one drain warpgroup per team + 4 auxiliary warps
 #ifndef BSK_TC_PROF
 #define BSK_TC_PROF 0
 #endif
 constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
-constexpr int REGS_TEAM = 144, REGS_AUX = 80;      // 384*144 + 128*80 = 512*128
+// 640 threads are launched with 96 registers each; setmaxnreg then moves registers from the
+// generator and auxiliary warpgroups to the drain warpgroups, which hold the second-level
+// accumulators: 256*72 + 256*144 + 128*40 <= 640*96
+constexpr int REGS_TEAM = 72, REGS_DRAIN = 144, REGS_AUX = 40;
 constexpr bool USE_OWN = false;   // lane v keeps row v of the chunk in registers across its team's units
-static_assert(NTEAMTHREADS * REGS_TEAM + 128 * REGS_AUX <= NTHREADS * (65536 / NTHREADS / 8 * 8), "register split");
-// D columns a unit may need, by position j in its team (units are dealt to the teams in order of
-// decreasing width): a pair (a <= b) only meets rows c >= b, so most units need few columns
-__host__ __device__ constexpr int cap(int j) { return j == 0 ? 40 : j == 1 ? 32 : 8; }
-__host__ __device__ constexpr int capoff(int j) { return j == 0 ? 0 : j == 1 ? 40 : 72; }
-constexpr int CAPSUM = 80;
-// TMEM columns: one accumulator per team, two A buffers (hi 32 + lo 32 columns) per team
-constexpr int TM_D = 0, TM_A = 128;
-static_assert(NTEAMS * MAXR <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
+static_assert(NTEAMTHREADS * (REGS_TEAM + REGS_DRAIN) + 128 * REGS_AUX <= NTHREADS * (65536 / NTHREADS / 8 * 8), "register split");
+static_assert(NTEAMTHREADS * (96 - REGS_TEAM) + 128 * (96 - REGS_AUX) >= NTEAMTHREADS * (REGS_DRAIN - 96), "setmaxnreg pool");
+// D columns a unit may need, by its position j in the team (units are sorted by decreasing width
+// and dealt round-robin to the teams): a pair (a <= b) only meets rows c >= b, so most units need
+// few columns
+__host__ __device__ constexpr int cap(int j) { return j == 0 ? 40 : j == 1 ? 32 : j == 2 ? 24 : 8; }
+__host__ __device__ constexpr int capoff(int j) { return j == 0 ? 0 : j == 1 ? 40 : j == 2 ? 72 : 96; }
+constexpr int CAPSUM = 104;       // per team
+// TMEM columns: one accumulator per unit (cap(j) columns) and two A buffers (hi 32 + lo 32
+// columns) per team
+constexpr int TM_D = 0, TM_A = 256;
+static_assert(NTEAMS * CAPSUM <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
 
 constexpr int RAW_STRIDE = TL * 4 + 16;            // bytes; +16 keeps lanes on distinct banks
 constexpr int RAW_BYTES = ((MAXR + 1) * RAW_STRIDE + 127) / 128 * 128;  // + one all-zero row for idle lanes
 constexpr int BIMG_BYTES = (TL / 4) * (MAXR / 8) * 128;   // one hi or lo image of a tile
 constexpr int OFF_BAR = 0;
-constexpr int OFF_RAW = 256;
+constexpr int OFF_RAW = 512;
 constexpr int OFF_BIMG = OFF_RAW + 2 * RAW_BYTES;  // [buf][hi|lo]
 constexpr int SMEM_BYTES = OFF_BIMG + 4 * BIMG_BYTES;
 static_assert(OFF_BIMG % 128 == 0, "operand images must be 128-byte aligned");
@@ -64,8 +73,8 @@ static_assert(OFF_BIMG % 128 == 0, "operand images must be 128-byte aligned");
 // barrier indices
 enum {
   RAW_FULL = 0, RAW_EMPTY = 2, B_FULL = 4, B_EMPTY = 6,
-  A_FULL = 8, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NTEAMS,
-  NBAR = D_EMPTY + NTEAMS
+  A_FULL = 8, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NTEAMS * UPT,
+  NBAR = D_EMPTY + NTEAMS * UPT
 };
 static_assert(NBAR * 8 + 8 <= OFF_RAW, "barrier area");
 
@@ -151,19 +160,19 @@ struct Params {
   int ucol0[NTEAMS * UPT];    // [team * UPT + j]: first D column the unit needs (multiple of 8)
   int uncol[NTEAMS * UPT];    //                   number of columns (multiple of 8, <= cap(j))
   const uint32_t* slot_tab;   // [team * UPT + j][4][32]: ra | rb << 8  (row index R = zero row)
-  double* partial;            // [cta][CAPSUM][NTEAMTHREADS]
+  double* partial;            // [cta][team][CAPSUM][128]
   int64_t partial_stride;
   int flush_chunks;
   long long* prof;            // PROF only: [team warp q=0: 8 counters per team][mma: 8 counters]
 };
 
-// Generator + drain team member; q = warp % 4 is the TMEM lane quarter.
+// Generator team member; q = warp % 4 is the TMEM lane quarter.  Pure producer: waits for a
+// free A buffer, writes the 128 x 32 pair products (hi, lo) of one unit, signals the MMA issuer.
 __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase,
                                           int team, int q, int lane) {
   const int my_nu = p.nu[team];
   const int R = p.nrows;
   uint32_t rb_off[UPT], ra_off[UPT];
-  int ncol[UPT];
   bool resident[UPT];   // warp-uniform: every lane's first row is row `lane` (or the lane is idle)
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
@@ -172,83 +181,18 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     ra_off[j] = (e & 0xFFu) * RAW_STRIDE;
     rb_off[j] = ((e >> 8) & 0xFFu) * RAW_STRIDE;
     resident[j] = USE_OWN && __all_sync(0xffffffffu, (e >> 16) & 1u);
-    // idle lanes of a resident slot multiply their own row by the zero row
-    ncol[j] = p.uncol[team * UPT + j];
   }
   const uint32_t own_off = (uint32_t)(lane < R ? lane : R) * RAW_STRIDE;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-  const uint32_t d_tmem = tbase + lane_sel + TM_D + (uint32_t)team * MAXR;
   const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
   const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
-  const uint32_t bar_dfull = bars + (D_FULL + team) * 8, bar_dempty = bars + (D_EMPTY + team) * 8;
-  float2 acc0[cap(0) / 2], acc1[cap(1) / 2], acc2[cap(2) / 2];
-#pragma unroll
-  for (int c = 0; c < cap(0) / 2; ++c) acc0[c] = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < cap(1) / 2; ++c) acc1[c] = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < cap(2) / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
-
   uint32_t n_gen = 0;     // units generated by this team so far
-  uint32_t n_drain = 0;   // units drained so far
-  int since_flush = 0;
-  double* my_partial = p.partial + (int64_t)blockIdx.x * p.partial_stride + team * 128 + q * 32 + lane;
-
-  long long t_raw = 0, t_gen = 0, t_aempty = 0, t_st = 0, t_dfull = 0, t_drain = 0, t_mark = 0;
+  long long t_raw = 0, t_gen = 0, t_aempty = 0, t_st = 0, t_mark = 0;
   auto tick = [&](long long& acc_t) {
     if constexpr (PROF) { const long long now = clock64(); acc_t += now - t_mark; t_mark = now; }
   };
-  auto drain_into = [&](auto jj, auto& acc) {
-    constexpr int J = decltype(jj)::value;
-    tc_wait(bar_dfull, n_drain & 1u);
-    tc_fence_after();
-    tick(t_dfull);
-    // two groups of 8 columns in flight at a time (register budget)
-#pragma unroll
-    for (int g0 = 0; g0 < cap(J) / 8; g0 += 2) {
-      if (g0 * 8 < ncol[J]) {
-        float2 v[2][4];
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol[J]) tmem_ld8v(d_tmem + (g0 + g) * 8, v[g]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol[J]) {
-            pin8(v[g]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[(g0 + g) * 4 + c] = __fadd2_rn(acc[(g0 + g) * 4 + c], v[g][c]);
-          }
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_dempty);
-    ++n_drain;
-    tick(t_drain);
-  };
-  auto drain_dyn = [&](int j) {   // statically indexed accumulators behind a warp-uniform switch
-    if (j == 0) drain_into(std::integral_constant<int, 0>{}, acc0);
-    else if (j == 1) drain_into(std::integral_constant<int, 1>{}, acc1);
-    else drain_into(std::integral_constant<int, 2>{}, acc2);
-  };
-  auto flush_arr = [&](auto jj, auto& acc) {
-    constexpr int J = decltype(jj)::value;
-#pragma unroll
-    for (int c = 0; c < cap(J) / 2; ++c)
-      if (2 * c < ncol[J]) {
-        atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c) * NTEAMTHREADS, (double)acc[c].x);
-        atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c + 1) * NTEAMTHREADS, (double)acc[c].y);
-        acc[c] = make_float2(0.f, 0.f);
-      }
-  };
-  auto flush = [&]() {
-    flush_arr(std::integral_constant<int, 0>{}, acc0);
-    flush_arr(std::integral_constant<int, 1>{}, acc1);
-    flush_arr(std::integral_constant<int, 2>{}, acc2);
-  };
-
   if constexpr (PROF) t_mark = clock64();
+
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
@@ -309,24 +253,107 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
           if (lane == 0) mbar_arrive(bar_afull + ab * 8);
           ++n_gen;
           tick(t_st);
-          // drain the unit generated before this one (its MMAs overlap this generation)
-          if (n_gen > 1) drain_dyn(j > 0 ? j - 1 : my_nu - 1);
         }
-      }
-      if (++since_flush == p.flush_chunks) {
-        flush();
-        since_flush = 0;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
   }
-  if (n_gen > 0) drain_dyn(my_nu - 1);
-  flush();
   if constexpr (PROF) {
     if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
       long long* o = p.prof + team * 8;
-      o[0] = t_raw; o[1] = t_gen; o[2] = t_aempty; o[3] = t_st; o[4] = t_dfull; o[5] = t_drain; o[6] = n_gen;
+      o[0] = t_raw; o[1] = t_gen; o[2] = t_aempty; o[3] = t_st; o[6] = n_gen;
+    }
+  }
+}
+
+// Drain warp (team, q): after each of its team's units has had its 12 MMAs, adds the accumulator of
+// TMEM lanes [32q, 32q+32) into fp32 registers (round to nearest) and releases the accumulator;
+// flushes to the float64 partials every flush_chunks chunks.
+template <int J>
+__device__ __forceinline__ void drain_unit(float2 (&acc)[cap(J) / 2], int ncol, uint32_t d_tmem, uint32_t bar_full,
+                                           uint32_t bar_empty, uint32_t parity, int lane, long long& prof_wait,
+                                           long long& prof_work) {
+  long long t0 = 0;
+  if constexpr (PROF) t0 = clock64();
+  tc_wait(bar_full, parity);
+  tc_fence_after();
+  if constexpr (PROF) { const long long now = clock64(); prof_wait += now - t0; t0 = now; }
+#pragma unroll
+  for (int g0 = 0; g0 < cap(J) / 8; g0 += 3) {   // up to three 8-column groups in flight
+    if (g0 * 8 < ncol) {
+      float2 v[3][4];
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol) tmem_ld8v(d_tmem + (g0 + g) * 8, v[g]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol) {
+          pin8(v[g]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[(g0 + g) * 4 + c] = __fadd2_rn(acc[(g0 + g) * 4 + c], v[g][c]);
+        }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_empty);
+  if constexpr (PROF) prof_work += clock64() - t0;
+}
+template <int J>
+__device__ __forceinline__ void flush_unit(float2 (&acc)[cap(J) / 2], int ncol, double* my_partial) {
+#pragma unroll
+  for (int c = 0; c < cap(J) / 2; ++c)
+    if (2 * c < ncol) {
+      atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c) * 128, (double)acc[c].x);
+      atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c + 1) * 128, (double)acc[c].y);
+      acc[c] = make_float2(0.f, 0.f);
+    }
+}
+template <int N>
+__device__ __forceinline__ void zero_acc(float2 (&acc)[N]) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) acc[c] = make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint32_t tbase, int team, int q, int lane) {
+  float2 a0[cap(0) / 2], a1[cap(1) / 2], a2[cap(2) / 2], a3[cap(3) / 2];
+  zero_acc(a0); zero_acc(a1); zero_acc(a2); zero_acc(a3);
+  const int my_nu = p.nu[team];
+  auto ncol = [&](int j) { return j < my_nu ? p.uncol[team * UPT + j] : 0; };
+  const uint32_t d_base = tbase + ((uint32_t)(q * 32) << 16) + TM_D + (uint32_t)team * CAPSUM;
+  const uint32_t bar_full = bars + (D_FULL + team * UPT) * 8, bar_empty = bars + (D_EMPTY + team * UPT) * 8;
+  double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * p.partial_stride + q * 32 + lane;
+  int since_flush = 0;
+  long long d_wait = 0, d_work = 0;
+  uint32_t n = 0;     // windows drained so far
+  auto flush = [&]() {
+    flush_unit<0>(a0, ncol(0), my_partial); flush_unit<1>(a1, ncol(1), my_partial);
+    flush_unit<2>(a2, ncol(2), my_partial); flush_unit<3>(a3, ncol(3), my_partial);
+  };
+#define BSK_TC_DRAIN(J, ACC)                                                                              \
+  if (J < my_nu)                                                                                          \
+    drain_unit<J>(ACC, ncol(J), d_base + capoff(J), bar_full + J * 8, bar_empty + J * 8, n & 1u, lane,    \
+                  d_wait, d_work);
+  for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+#pragma unroll 1
+    for (int c = 0; c < NCH / WIN; ++c) {
+      BSK_TC_DRAIN(0, a0) BSK_TC_DRAIN(1, a1) BSK_TC_DRAIN(2, a2) BSK_TC_DRAIN(3, a3)
+      ++n;
+      if ((since_flush += WIN) >= p.flush_chunks) {
+        flush();
+        since_flush = 0;
+      }
+    }
+  }
+#undef BSK_TC_DRAIN
+  flush();
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
+      p.prof[(NTEAMS + 1 + team) * 8 + 0] = d_wait;
+      p.prof[(NTEAMS + 1 + team) * 8 + 1] = d_work;
+      p.prof[(NTEAMS + 1 + team) * 8 + 2] = n;
     }
   }
 }
@@ -338,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   const uint32_t bars = smem_u32(bar_ptr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = p.nrows, N = p.ncols;
-  constexpr int W_TMA = NTEAMS * 4, W_MMA = W_TMA + 1;
+  constexpr int W_DRAIN = NTEAMS * 4, W_TMA = 2 * W_DRAIN, W_MMA = W_TMA + 1;
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
       mbar_init(&bar_ptr[A_FULL + b], 4);
       mbar_init(&bar_ptr[A_EMPTY + b], 1);
     }
-    for (int b = 0; b < NTEAMS; ++b) {
+    for (int b = 0; b < NTEAMS * UPT; ++b) {
       mbar_init(&bar_ptr[D_FULL + b], 1);
       mbar_init(&bar_ptr[D_EMPTY + b], 4);
     }
@@ -373,9 +400,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp < NTEAMS * 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_TEAM));
+  if (warp < W_DRAIN) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_TEAM));
     team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);
+  } else if (warp < W_TMA) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
+    drain_loop(p, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     if (warp == W_TMA) {
@@ -418,6 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
         const uint32_t d_hi32 = (uint32_t)(make_desc(img_hi, lbo, 128u) >> 32);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          const uint32_t n_win = (uint32_t)it * (NCH / WIN) + (uint32_t)(c / WIN);
 #pragma unroll
           for (int j = 0; j < UPT; ++j) {
 #pragma unroll
@@ -428,10 +459,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
               if constexpr (PROF) m_mark = clock64();
               tc_wait(bars + (A_FULL + team * 2 + ab) * 8, (n >> 1) & 1u);
               if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
-              tc_wait(bars + (D_EMPTY + team) * 8, (n & 1u) ^ 1u);
+              if (c % WIN == 0)    // first chunk of a window: the unit's accumulator must have been drained
+                tc_wait(bars + (D_EMPTY + team * UPT + j) * 8, (n_win & 1u) ^ 1u);
               tc_fence_after();
               if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
-              const uint32_t d = tbase + TM_D + (uint32_t)team * MAXR;
+              const uint32_t d = tbase + TM_D + (uint32_t)team * CAPSUM + capoff(j);
               const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
               const uint32_t id = idesc[team * UPT + j];
               const uint32_t o0 = coff[team * UPT + j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
@@ -439,13 +471,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
 #pragma unroll
                 for (int ks = 0; ks < CH / 8; ++ks) {
                   const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
-                  if (ks == 0) mma_tf32_ts2<0>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);   // P_lo * C_hi
+                  if (ks == 0 && c % WIN == 0) mma_tf32_ts2<0>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);   // P_lo * C_hi
                   else mma_tf32_ts2<1>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);
                   mma_tf32_ts2<1>(d, a + ks * 8, dl_lo + o, d_hi32, id);                       // P_hi * C_lo
                   mma_tf32_ts2<1>(d, a + ks * 8, dh_lo + o, d_hi32, id);                       // P_hi * C_hi
                 }
                 tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
-                tc_commit(bars + (D_FULL + team) * 8);
+                if (c % WIN == WIN - 1) tc_commit(bars + (D_FULL + team * UPT + j) * 8);
               }
               __syncwarp();
               if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
