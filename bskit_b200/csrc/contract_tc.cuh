@@ -31,7 +31,7 @@ namespace tc {
 constexpr int CH = 32;            // cells per chunk = K extent of one unit
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
-constexpr int WIN = 2;            // chunks accumulated in TMEM before a drain (divides NCH): the
+constexpr int WIN = 4;            // chunks accumulated in TMEM before a drain (divides NCH): the
                                   // accumulator truncates, so the window bounds the bias (~3.5e-7 per chunk)
 static_assert(NCH % WIN == 0, "window");
 constexpr int MAXR = 40;          // rows (N <= 40)
