@@ -30,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TC_DRAM_BYTES = 24.6e9      # ncu dram read + write of tc_contract_kernel at 512^3, S=40 (profiles/)
 METRIC = "s per 512^3 all-triangle bispectrum"
 
 
@@ -225,12 +226,12 @@ def main():
         del tmp
     accum = nat.F32 if args.accum == "f32" else nat.F64
 
-    def make(policy, tensor=False):
+    def make(policy, tensor=None):
         g = eng.choose_grid(nmesh, syn.BOX, edges[:, 1].max(), policy, world)
         gn = eng.choose_grid(nmesh, syn.BOX, edges[:, 1].max(), "auto", world)
         e_data = eng.Engine(g, syn.BOX, nat.F32, device=dev, accum_precision=accum)
-        if tensor:
-            e_data.backend.contraction_path = 1     # tcgen05 path (include/bskit_b200.h, bsk_cplan_set_path)
+        if tensor is not None:                      # None: the library default
+            e_data.backend.contraction_path = 1 if tensor else 0   # include/bskit_b200.h, bsk_cplan_set_path
         e_norm = eng.Engine(gn, syn.BOX, nat.F64, device=dev)
         return e_data, e_norm
 
@@ -246,7 +247,7 @@ def main():
         eng._mark(marks, "norm_done", e_data)
         return b, ntri_v, kmean
 
-    def timed(policy, steps, warmup, with_clocks=False, tensor=False):
+    def timed(policy, steps, warmup, with_clocks=False, tensor=None):
         e_data, e_norm = make(policy, tensor)
         slab = e_data.local_slab(host)
         for _ in range(warmup):
@@ -304,8 +305,9 @@ def main():
                               "stages_ms": full["stages_ms"], "gpu_launches": full["launches"]}))
         return
     auto = timed("auto", args.steps, args.warmup)
-    # the same step with the contraction on the tensor cores (opt-in path, reported beside the default)
-    tens = timed("full", 2, 1, tensor=True) if accum == nat.F32 else None
+    # the same step with the other contraction kernel (tensor cores <-> FP32 pipe), reported beside the default
+    default_tensor = full["schedule"] == "tensor"
+    alt = timed("full", 2, 1, tensor=not default_tensor) if accum == nat.F32 else None
 
     # ---- e2e: the user-facing API from (pinned) host memory, result back on the host
     def e2e_once():
@@ -363,19 +365,37 @@ def main():
     issued = full["cplan"]["nblocks"] * 80.0 * 2.0 * cells if full["cplan"] else None
     clk = (full["clocks"] or {}).get("sm_mhz") or 1900.0
     fp32_peak = 72.5e12 * clk / 1965.0        # measured by scripts/dev/ffma_probe.cu at 1965 MHz
-    roofline = {"kernel": "tile_contract_kernel<float,%s>" % ("float" if accum == nat.F32 else "double"),
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
-                # kernel at this exact configuration (profiles/r1_tile_contract_packed_ncu_raw.csv)
-                "traffic": 21.513e9 if (nmesh == 512 and len(edges) == 40 and world == 1) else None,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_contract * 1e3,
-                "note": "the kernel is FP32-FMA-pipe bound, not HBM bound: see fp32_pipe",
-                "fp32_pipe": {"issued_flops_per_launch": issued, "useful_flops_per_launch": useful_flops,
-                              "issued_tflops": (issued / t_contract / 1e12) if issued else None,
-                              "peak_tflops_measured_ffma_probe": fp32_peak / 1e12,
-                              "frac_issued": (issued / t_contract / fp32_peak) if issued else None}}
+    # issued tensor-core work: 3 MMAs (P_lo*C_hi, P_hi*C_lo, P_hi*C_hi) of 2*128*N flops per cell and unit;
+    # the N of the units of the S=40 all-triangle schedule sum to 184
+    issued_tc = 6.0 * 128.0 * 184.0 * cells if (len(edges) == 40 and ntri == 6730) else None
+    tf32_peak = 741.0            # TFLOP/s, cuBLAS TF32 8192^3 measured on this pool's B200 (profiles/r1_extra_peaks.txt)
+    fp32_info = {"issued_flops_per_launch": issued, "useful_flops_per_launch": useful_flops,
+                 "peak_tflops_measured_ffma_probe": fp32_peak / 1e12}
+    if default_tensor:
+        roofline = {"kernel": "tc_contract_kernel (tcgen05.mma kind::tf32, 3xTF32, pair products in TMEM)",
+                    "bound": "tensor", "achieved": (issued_tc / t_contract / 1e12) if issued_tc else None,
+                    "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": (issued_tc / t_contract / 1e12 / tf32_peak) if issued_tc else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                    # at this configuration (profiles/r1_tc_contract_ncu_summary.txt)
+                    "traffic": TC_DRAM_BYTES if (nmesh == 512 and len(edges) == 40 and world == 1) else None,
+                    "peak_source": "measured TF32 cuBLAS 8192^3 (profiles/r1_extra_peaks.txt); MEASURED_PEAKS.json holds bf16 only",
+                    "issued_flops_per_launch": issued_tc, "useful_flops_per_launch": useful_flops,
+                    "algorithmic_bytes_per_launch": alg_bytes, "hbm_GBps": achieved, "kernel_ms": t_contract * 1e3,
+                    "note": "bounded by operand generation (shared-memory reads of the two rows of every pair) "
+                            "rather than the tensor pipe: see DESIGN.md"}
+    else:
+        roofline = {"kernel": "tile_contract_kernel<float,%s>" % ("float" if accum == nat.F32 else "double"),
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+                    # kernel at this exact configuration (profiles/r1_tile_contract_packed_ncu_raw.csv)
+                    "traffic": 21.513e9 if (nmesh == 512 and len(edges) == 40 and world == 1) else None,
+                    "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_contract * 1e3,
+                    "note": "the kernel is FP32-FMA-pipe bound, not HBM bound: see fp32_pipe",
+                    "fp32_pipe": dict(fp32_info, issued_tflops=(issued / t_contract / 1e12) if issued else None,
+                                      frac_issued=(issued / t_contract / fp32_peak) if issued else None)}
     shells_bytes = float(len(edges)) * full["ncells"] * (8 * (nmesh // 2 + 1) / nmesh + 4)
     stage_roofs = {"shells": {"algorithmic_bytes": shells_bytes,
                               "achieved_GBps": shells_bytes / (full["stages_ms"]["shells"] * 1e-3) / 1e9,
@@ -408,21 +428,24 @@ def main():
                       "note": "exact band-limited evaluation (library default); same outputs"},
         "checks": {"api_vs_engine_max_abs_over_rms": api_agree},
     }
-    if tens is not None:
-        t_tc = tens["stages_ms"]["contract"] * 1e-3
-        # issued: 3 MMAs (P_lo*C_hi, P_hi*C_lo, P_hi*C_hi) of 2*128*N flops per cell and unit;
-        # sum of N over the units of the S=40 all-triangle schedule = 184
-        issued_tc = 6.0 * 128.0 * 184.0 * cells if (len(edges) == 40 and ntri == 6730) else None
-        line["tensor_path"] = {
-            "kernel": "tc_contract_kernel (tcgen05.mma kind::tf32, 3xTF32, A operand in TMEM)",
-            "schedule": tens["schedule"], "ms_per_step": tens["ms_per_step"],
-            "contract_ms": t_tc * 1e3, "fp32_pipe_contract_ms": t_contract * 1e3,
-            "max_abs_diff_vs_fp32_pipe_over_rms": float(np.max(np.abs(tens["out"][0] - bf)) / rms),
-            "roofline": {"bound": "tensor", "achieved": (issued_tc / t_tc / 1e12) if issued_tc else None,
-                         "peak": 741.0, "unit": "TFLOP/s",
-                         "frac": (issued_tc / t_tc / 1e12 / 741.0) if issued_tc else None,
-                         "peak_source": "measured TF32 cuBLAS 8192^3 on this pool's B200 (profiles/r1_extra_peaks.txt)"},
-            "note": "opt-in (BSKIT_B200_CONTRACTION=tensor): bounded by operand generation, see DESIGN.md"}
+    if alt is not None:
+        t_alt = alt["stages_ms"]["contract"] * 1e-3
+        info = {"schedule": alt["schedule"], "ms_per_step": alt["ms_per_step"], "contract_ms": t_alt * 1e3,
+                "default_contract_ms": t_contract * 1e3,
+                "max_abs_diff_vs_default_over_rms": float(np.max(np.abs(alt["out"][0] - bf)) / rms)}
+        if default_tensor:
+            info.update(kernel="tile_contract_kernel<float,float> (FP32 pipe, packed FFMA2; BSKIT_B200_CONTRACTION=fp32)",
+                        fp32_pipe=dict(fp32_info, issued_tflops=(issued / t_alt / 1e12) if issued else None,
+                                       frac_issued=(issued / t_alt / fp32_peak) if issued else None),
+                        note="exact round-to-nearest products: error floor ~5e-8 of max|B| instead of ~1e-6")
+        else:
+            info.update(kernel="tc_contract_kernel (tcgen05.mma kind::tf32, 3xTF32, pair products in TMEM; "
+                               "BSKIT_B200_CONTRACTION=tensor)",
+                        roofline={"bound": "tensor", "achieved": (issued_tc / t_alt / 1e12) if issued_tc else None,
+                                  "peak": tf32_peak, "unit": "TFLOP/s",
+                                  "frac": (issued_tc / t_alt / 1e12 / tf32_peak) if issued_tc else None},
+                        note="3xTF32 with truncating tensor-core accumulators: ~1e-6 relative instead of ~5e-8")
+        line["other_contraction_path"] = info
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -230,8 +230,10 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 pr = __fmul2_rn(pa[i], pb[i]);
-              const float2 ph = make_float2(__uint_as_float(__float_as_uint(pr.x) & 0xFFFFE000u),
-                                            __uint_as_float(__float_as_uint(pr.y) & 0xFFFFE000u));
+              // hi = product rounded to nearest tf32 (11 bits): the low part is then sign-symmetric and
+              // at most 2^-12 |P|, so the tensor core's truncation of it costs 2^-23 instead of 2^-22
+              const float2 ph = make_float2(__uint_as_float((__float_as_uint(pr.x) + 0x1000u) & 0xFFFFE000u),
+                                            __uint_as_float((__float_as_uint(pr.y) + 0x1000u) & 0xFFFFE000u));
               const float2 pl = __ffma2_rn(ph, make_float2(-1.f, -1.f), pr);   // exact
               hi[2 * i] = __float_as_uint(ph.x); hi[2 * i + 1] = __float_as_uint(ph.y);
               lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);

@@ -182,9 +182,10 @@ class NativeBackend:
         self.info = nat.Info()
         nat.check(self.lib.bsk_plan_info(handle, C.byref(self.info)), "bsk_plan_info")
         self._cplans = {}
-        #: 0 = FP32-pipe tile kernel (default), 1 = tcgen05 tensor cores for eligible dense lists
-        #: (include/bskit_b200.h, bsk_cplan_set_path); BSKIT_B200_CONTRACTION=tensor selects 1
-        self.contraction_path = 1 if os.environ.get("BSKIT_B200_CONTRACTION", "") == "tensor" else 0
+        #: 1 = tcgen05 tensor cores for eligible dense lists (default; 3xTF32, ~1e-6 relative),
+        #: 0 = FP32-pipe tile kernel everywhere (exact round-to-nearest products, ~5e-8;
+        #: BSKIT_B200_CONTRACTION=fp32).  include/bskit_b200.h, bsk_cplan_set_path
+        self.contraction_path = 0 if os.environ.get("BSKIT_B200_CONTRACTION", "") == "fp32" else 1
         self.last_path = 0
 
     def close(self):

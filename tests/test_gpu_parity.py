@@ -269,9 +269,20 @@ def test_module_functions(bk, syn):
     np.testing.assert_allclose(B, wb[0] / wn2[0], rtol=1e-9)
 
 
-def test_band_limited_grid_equals_full_grid_256(bk, syn):
+# Error floors of the two contraction kernels (|dB| <= 1e-5 |B| + floor * rms(B)): the FP32-pipe
+# kernel multiplies float32 fields exactly (round to nearest) -> the float32 storage floor of
+# 1e-6; the tensor-core kernel (library default for dense lists) carries 22-23 bit operands
+# (3xTF32) -> measured 3e-6 on the triangles whose |B| is far below rms(B).
+FLOOR = {"tensor": 5e-6, "fp32": 1e-6}
+
+
+@pytest.mark.parametrize("path", ["tensor", "fp32"])
+def test_band_limited_grid_equals_full_grid_256(bk, syn, path, monkeypatch):
     """Size-independent property at a size the oracle cannot sweep quickly: the exact
-    band-limited evaluation (grid='auto') and the mesh's own grid (grid='full') agree."""
+    band-limited evaluation (grid='auto') and the mesh's own grid (grid='full') agree, with
+    either contraction kernel."""
+    monkeypatch.setenv("BSKIT_B200_CONTRACTION", path)
+    bk.clear_cache()
     n, nb = 256, 24
     kmin, kmax, dk = syn.bench_bins(nb)
     mesh = syn.lognormal_mesh(n, seed=1)
@@ -280,13 +291,14 @@ def test_band_limited_grid_equals_full_grid_256(bk, syn):
         fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid=grid)
         res[grid] = fb.measure_bispectrum_faster(0, 10 ** 9)["B"]
         fb.close()
-    assert_b_close(res["auto"], res["full"])
+    assert_b_close(res["auto"], res["full"], atol_rms=FLOOR[path])
     # spot-check 6 triangles against the oracle at full size
     edges = orc.bin_edges(kmin, kmax, dk)
     _, idx = orc.triangles_all(edges, 1)
     pick = np.linspace(0, len(idx) - 1, 6).astype(int)
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx[pick], workers=8)
-    assert_b_close(res["full"][pick], want)
+    assert_b_close(res["full"][pick], want, atol_rms=FLOOR[path])
+    bk.clear_cache()
 
 
 def test_float64_accumulation_mode_is_tighter(bk, syn):
@@ -390,12 +402,12 @@ def test_c2_256_lognormal_all_triangles_auto_plus_norm(bk, syn):
     fa = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="auto")
     ga = fa.measure_bispectrum_faster(0, 10 ** 9)
     fa.close()
-    assert_b_close(ga["B"], got["B"])                       # band-limited == mesh grid, all 6730
+    assert_b_close(ga["B"], got["B"], atol_rms=FLOOR["tensor"])   # band-limited == mesh grid, all 6730
     idx = np.asarray(fb.k_indices)
     pick = np.linspace(0, len(idx) - 1, 6).astype(int)
     want = orc.measure_unnormalized([mesh], syn.BOX, edges, idx[pick], workers=_ncores())
     rms = np.sqrt(np.mean(got["B"] ** 2))
-    assert np.all(np.abs(got["B"][pick] - want) <= RTOL_B * np.abs(want) + 1e-6 * rms)
+    assert np.all(np.abs(got["B"][pick] - want) <= RTOL_B * np.abs(want) + FLOOR["tensor"] * rms)
     wn, wk = orc.measure_gridinfo(n, syn.BOX, edges, idx[pick], workers=_ncores())
     assert np.array_equal(gi["N_tri"][pick], np.rint(wn))
     np.testing.assert_allclose(gi["k_mean"][pick], wk, rtol=1e-9)
@@ -597,6 +609,7 @@ def test_tensor_core_contraction_path(bk, syn):
     assert len(dense) >= 256
     want = np.array([(t64[a] * t64[b] * t64[c]).sum().item() for a, b, c in dense])
     scale = np.abs(want).max()
+    e.backend.contraction_path = 0
     tile = e.contract(table, dense)[0]
     assert e.last_schedule == "tile"
     e.backend.contraction_path = 1
