@@ -150,8 +150,8 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, roun
 
 /* Contraction path of a schedule.  path 0 (default): FP32-pipe tile kernel (packed FFMA2, exact
  * round-to-nearest products).  path 1: tcgen05 tensor cores, 3xTF32 operands with the pair
- * products written to TMEM, accumulators drained every 32 cells (relative error ~4e-7 instead of
- * ~5e-8).  Path 1 is used only when the list is eligible: float32 fields and products, one job
+ * products written to TMEM, accumulators drained every 128 cells (relative error ~8e-7 instead of
+ * ~5e-8; the Python host selects it by default).  Path 1 is used only when the list is eligible: float32 fields and products, one job
  * with zero offsets, at most 40 rows, at least 256 triangles, ncells a multiple of 128;
  * otherwise bsk_contract runs path 0.  bsk_cplan_path: out = {tensor-core units of the
  * schedule (0: not eligible), requested path, path the last bsk_contract call ran}. */
