@@ -636,20 +636,27 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
         rows = pos[tri]
         job_off = np.asarray(job_seg_off, dtype=np.int64) * seg
         m = engine.grid.neval
-        if symmetric and engine.world == 1 and m % 2 == 0 and table.shape[1] == m ** 3:
+        mxl = table.shape[1] // (m * m)
+        if symmetric and m % 2 == 0 and table.shape[1] == mxl * m * m and (engine.world > 1 or mxl == m):
             # Unit-amplitude and |k|-weighted shells depend on |k| only, so they are even in every
-            # axis: f(x,y,z) = f(-x,y,z) = ...  The sum over the grid is the sum over the octant
-            # [0, M/2]^3 with multiplicity w = wx wy wz (w_axis = 1 on the planes 0 and M/2, else 2).
+            # axis: f(x,y,z) = f(-x,y,z) = ...  The sum over the grid is the sum over [0, M/2] per
+            # mirrored axis with multiplicity w = prod w_axis (1 on the planes 0 and M/2, else 2).
             # Scaling every field by w^(1/3) puts the weight into the triple product, so one
-            # contraction over (M/2+1)^3 cells replaces the full-grid one (8x fewer cells).
+            # contraction over the reduced cells replaces the full-grid one: all three axes on one
+            # GPU (8x fewer cells), y and z on this rank's x-slab otherwise (4x fewer).
             h = m // 2 + 1
             w1 = torch.full((h,), 2.0, dtype=torch.float64, device=table.device)
             w1[0] = 1.0
             w1[h - 1] = 1.0
-            w3 = (w1[:, None, None] * w1[None, :, None] * w1[None, None, :]) ** (1.0 / 3.0)
-            ncell_o = (h ** 3 + 3) // 4 * 4
+            if engine.world == 1:
+                nx, wx = h, w1
+            else:
+                nx, wx = mxl, torch.ones(mxl, dtype=torch.float64, device=table.device)
+            w3 = (wx[:, None, None] * w1[None, :, None] * w1[None, None, :]) ** (1.0 / 3.0)
+            nred = nx * h * h
+            ncell_o = (nred + 3) // 4 * 4
             octant = torch.zeros((table.shape[0], ncell_o), dtype=table.dtype, device=table.device)
-            octant[:, :h ** 3] = (table.view(-1, m, m, m)[:, :h, :h, :h] * w3.to(table.dtype)).reshape(table.shape[0], -1)
+            octant[:, :nred] = (table.view(-1, mxl, m, m)[:, :nx, :h, :h] * w3.to(table.dtype)).reshape(table.shape[0], -1)
             ofields = []
             for sidx in range(nseg):
                 ofields += [octant[sidx * nb + r] for r in range(nb)] + [octant[sidx * nb]] * (seg - nb)
