@@ -10,17 +10,22 @@
 // anyway -- are written straight into TMEM and never touch shared memory.
 //
 // Numerics.  3xTF32: P = F_a*F_b (fp32, RN) is split P = P_hi + P_lo, F_c = C_hi + C_lo with
-// 11-bit pieces, and D += P_lo*C_hi + P_hi*C_lo + P_hi*C_hi.  The tensor core truncates its fp32
-// accumulator (round toward zero, profiles/r1_tensor_core_rounding_probe.txt), which would bias a
-// long heavily-cancelling sum, so an accumulator lives in TMEM for ONE 32-cell chunk only
-// (12 MMAs); it is then drained into fp32 registers with round-to-nearest adds, and those are
-// flushed into float64 partials every few hundred chunks.  Measured: 3.5e-7 of max|sum| against
-// a float64 reference (FP32-pipe kernel: 5e-8).
+// 11-bit pieces (hi parts rounded to nearest), and D += P_lo*C_hi + P_hi*C_lo + P_hi*C_hi.  The
+// tensor core truncates its fp32 accumulator (round toward zero,
+// profiles/r1_tensor_core_rounding_probe.txt), which biases a long heavily-cancelling sum
+// (~3.5e-7 per 32 cells accumulated), so an accumulator lives in TMEM for one window of WIN
+// chunks only; it is then drained into fp32 registers with round-to-nearest adds, and those are
+// flushed into float64 partials every few hundred chunks.  TMEM reads run at 64 B/cycle/SM, so
+// the window is a speed/bias trade (WIN = 1 / 2 / 4: 70.7 / 52.3 / 47.6 ms, 3.7e-7 / 6.0e-7 /
+// 9.2e-7 of max|sum| at 512^3, S = 40; FP32-pipe kernel: 71 ms, 5e-8).
 //
-// Roles (one CTA per SM, persistent over tiles of 128 cells):
-//   NTEAMS x 4 warps generator+drain teams; warp q of a team owns TMEM lanes [32q, 32q+32)
+// Roles (640 threads, one CTA per SM, persistent over tiles of 128 cells; setmaxnreg 72/144/40):
+//   2 x 4 warps      generator teams, pure producers: warp q of a team owns TMEM lanes
+//                    [32q, 32q+32) and writes the hi / lo pair products of one unit (128 pair rows x
+//                    32 cells) into one of the team's two A buffers
+//   2 x 4 warps      drain warpgroups, one per team: own the second-level accumulators
 //   1 warp           TMA producer: raw [row][cell] tiles, cp.async.bulk + mbarrier
-//   1 warp           MMA issuer (one elected lane)
+//   1 warp           MMA issuer (one elected lane): 12 MMAs per unit into the unit's own accumulator
 //   2 warps          convert the raw tile to the B operand images (hi / lo, K-major core
 //                    matrices: 8 rows x 16 bytes)
 #pragma once
