@@ -380,6 +380,8 @@ def main():
                     # at this configuration (profiles/r1_tc_contract_ncu_summary.txt)
                     "traffic": TC_DRAM_BYTES if (nmesh == 512 and len(edges) == 40 and world == 1) else None,
                     "peak_source": "measured TF32 cuBLAS 8192^3 (profiles/r1_extra_peaks.txt); MEASURED_PEAKS.json holds bf16 only",
+                    "frac_of_half_measured_bf16_peak": (issued_tc / t_contract / 1e12 / (0.5 * float(peaks["bf16_tflops"])))
+                    if (issued_tc and peaks.get("bf16_tflops")) else None,
                     "issued_flops_per_launch": issued_tc, "useful_flops_per_launch": useful_flops,
                     "algorithmic_bytes_per_launch": alg_bytes, "hbm_GBps": achieved, "kernel_ms": t_contract * 1e3,
                     "note": "bounded by operand generation (shared-memory reads of the two rows of every pair) "
