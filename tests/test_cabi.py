@@ -52,6 +52,13 @@ def test_argument_errors_are_reported_not_crashes():
     rc = lib.bsk_plan_create(C.byref(handle), C.byref(geom), _native.dptr(t), _native.dptr(t),
                              _native.dptr(t), None)
     assert rc == -1 and b"nmesh" in lib.bsk_last_error()
+    # entry points added for the tensor-core path and for particle painting validate their arguments
+    # before any CUDA call
+    assert lib.bsk_cplan_set_path(None, 1) == -1 and b"bsk_cplan_set_path" in lib.bsk_last_error()
+    assert lib.bsk_cplan_path(None, None) == -1
+    box = np.array([100.0, 100.0, 100.0])
+    assert lib.bsk_paint_cic(None, 0, 10, 16, _native.dptr(box), None, None) == -1
+    assert b"bsk_paint_cic" in lib.bsk_last_error()
 
 
 def test_no_cpu_fallback():
