@@ -486,7 +486,10 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
 // "slot" s = 0..16 pairs it with row (v + s) mod 32, which covers every pair of rows < 32 once;
 // rows >= 32 get one slot each (warp-uniform partner), pairs among rows >= 32 are packed into
 // slots that load both rows.  Four slots (one per TMEM lane quarter) form a 128-row unit.
-static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows) {
+// Host part: fills cp->tc_* and the two tables; no CUDA calls (bsk_tc_schedule_info and the CPU
+// tests use it without a device).
+static bool build_tc_schedule_host(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows,
+                                   std::vector<uint32_t>& tab, std::vector<int>& tri_slot) {
   using namespace bsk::tc;
   if (nrows > MAXR || ntri < 256) return false;
   const int R = nrows;
@@ -555,7 +558,7 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
   // widest units first, dealt alternately to the two teams; position j must fit cap(j)
   std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.ncol > y.ncol; });
   const int ncols = (R + 7) / 8 * 8;
-  std::vector<uint32_t> tab((size_t)NTEAMS * UPT * 128, idle | (1u << 16));
+  tab.assign((size_t)NTEAMS * UPT * 128, idle | (1u << 16));
   for (int t = 0; t < NTEAMS; ++t) cp->tc_nu[t] = 0;
   std::unordered_map<int, int> slot_pos;   // slot id -> (team * UPT + j) * 4 + q
   for (int u = 0; u < nunits; ++u) {
@@ -571,7 +574,7 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
       for (int l = 0; l < 32; ++l) tab[(size_t)pos * 32 + l] = sr.s->e[l];
     }
   }
-  std::vector<int> tri_slot((size_t)ntri);
+  tri_slot.assign((size_t)ntri, 0);
   for (int t = 0; t < ntri; ++t) {
     const size_t pi = (size_t)ta[t] * R + tb[t];
     const int pos = slot_pos[pair_slot[pi]], lane = pair_lane[pi];
@@ -579,6 +582,14 @@ static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int 
     tri_slot[t] = ((team * CAPSUM) + capoff(j) + tcc[t] - cp->tc_col0[tj]) * 128 + q * 32 + lane;
   }
   cp->tc_units = nunits; cp->tc_ncols = ncols;
+  return true;
+}
+
+static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows) {
+  using namespace bsk::tc;
+  std::vector<uint32_t> tab;
+  std::vector<int> tri_slot;
+  if (!build_tc_schedule_host(cp, ntri, rows, nrows, tab, tri_slot)) return false;
   if (cudaMalloc((void**)&cp->d_tc_slots, sizeof(uint32_t) * tab.size()) != cudaSuccess) return false;
   cudaMemcpy(cp->d_tc_slots, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice);
   if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int) * (size_t)ntri) != cudaSuccess) return false;
@@ -725,6 +736,34 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]) {
   out[1] = cp->split;
   out[2] = cp->rounds;
   out[3] = kThreads;
+  return BSK_OK;
+}
+
+int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6]) {
+  using namespace bsk::tc;
+  BSK_REQUIRE(rows && out && ntri > 0 && nrows > 0, "bsk_tc_schedule_info: bad argument");
+  for (int i = 0; i < 3 * ntri; ++i)
+    BSK_REQUIRE(rows[i] >= 0 && rows[i] < nrows, "bsk_tc_schedule_info: row index %d outside [0,%d)", rows[i], nrows);
+  bsk_cplan tmp;
+  std::vector<uint32_t> tab;
+  std::vector<int> tri_slot;
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  if (!build_tc_schedule_host(&tmp, ntri, rows, nrows, tab, tri_slot)) return BSK_OK;   // not eligible
+  std::vector<int> sorted(tri_slot);
+  std::sort(sorted.begin(), sorted.end());
+  int64_t distinct = sorted.empty() ? 0 : 1;
+  for (size_t i = 1; i < sorted.size(); ++i) distinct += sorted[i] != sorted[i - 1];
+  int64_t cols = 0, pair_rows = 0, in_range = 1;
+  for (int i = 0; i < NTEAMS * UPT; ++i) cols += tmp.tc_ncol[i];
+  const uint32_t idle = (uint32_t)nrows | ((uint32_t)nrows << 8);
+  for (uint32_t e : tab) pair_rows += (e & 0xFFFFu) != idle;
+  for (int t = 0; t < ntri; ++t) in_range &= tri_slot[t] >= 0 && tri_slot[t] < NTEAMS * CAPSUM * 128;
+  out[0] = tmp.tc_units;      // 128-row units
+  out[1] = distinct;          // distinct accumulator slots the triangles read (== ntri when injective)
+  out[2] = cols;              // sum over units of the accumulator columns (MMA cost ~ 128 * cols)
+  out[3] = pair_rows;         // pair rows generated (<= 128 * units)
+  out[4] = in_range;
+  out[5] = (int64_t)NTEAMS * CAPSUM * 128;
   return BSK_OK;
 }
 

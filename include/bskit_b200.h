@@ -156,6 +156,11 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, roun
  * otherwise bsk_contract runs path 0.  bsk_cplan_path: out = {tensor-core units of the
  * schedule (0: not eligible), requested path, path the last bsk_contract call ran}. */
 int bsk_cplan_set_path(bsk_cplan* cp, int path);
+/* Host only (no device needed): the tensor-core schedule bsk_cplan_create builds for a list.
+ * out = {128-row units (0: list not eligible), distinct accumulator slots read by the triangles
+ * (== ntri), sum of the units' accumulator columns, pair rows generated, all slots in range,
+ * slots per CTA}. */
+int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6]);
 int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]);
 
 /* sums[j][t] = sum over local cells x of

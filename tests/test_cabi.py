@@ -68,3 +68,40 @@ def test_no_cpu_fallback():
     g = eng.choose_grid(16, 100.0, 0.2, "full")
     with pytest.raises(_native.NativeError):
         eng.Engine(g, 100.0, _native.F32, device=torch.device("cpu"))
+
+
+def test_tensor_core_schedule_is_injective_and_pruned():
+    """Host logic of the tcgen05 contraction (no device): every triangle of a dense list reads
+    its own accumulator slot (pair row x column), the S=40 all-triangle list needs 7 units whose
+    column counts sum to 184 (vs 7 x 40 dense), and lists that do not fit are reported ineligible."""
+    import ctypes as C
+    import numpy as np
+    from bskit_b200 import _native
+    from bskit_b200.bins import generate_triangle_bin_list
+    lib = _native.lib()
+
+    def info(rows, nrows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = (C.c_int64 * 6)()
+        assert lib.bsk_tc_schedule_info(len(rows), rows.ctypes.data_as(C.POINTER(C.c_int32)), nrows, out) == 0
+        return list(out)
+
+    kf = 2 * np.pi / 1000.0
+    for nb, units, cols in ((40, 7, 184), (24, 5, None), (12, 3, None)):
+        idx = generate_triangle_bin_list(kmin=0.5 * kf, kmax=(nb + 1.0) * kf, dk=kf, return_indices=True)
+        assert idx.max() == nb - 1
+        got = info(idx, (nb + 3) // 4 * 4)
+        assert got[0] == units, got
+        assert got[1] == len(idx) and got[4] == 1          # injective, in range
+        if cols:
+            assert got[2] == cols
+        assert got[3] == nb * (nb + 1) // 2 and got[3] <= 128 * units     # one pair row per row pair
+    # random dense list over 40 rows in arbitrary row order: still injective
+    rng = np.random.default_rng(0)
+    tri = np.array([[a, b, c] for a in range(40) for b in range(a, 40) for c in range(b, 40) if (a + b + c) % 3 == 0])
+    tri = np.array([rng.permutation(t) for t in tri])
+    got = info(tri, 40)
+    assert got[0] > 0 and got[1] == len(tri) and got[4] == 1
+    # not eligible: too many rows, too few triangles
+    assert info(np.array([[a, a, a] for a in range(80)] * 4), 80)[0] == 0
+    assert info(np.array([[0, 1, 2]]), 4)[0] == 0
