@@ -396,6 +396,7 @@ tri_stream_reduce_kernel(const T* const* __restrict__ rowptr, const int* __restr
 }  // namespace bsk
 
 #include "contract_tc.cuh"
+#include "tc_schedule.h"
 
 // split each block's tile over `split` threads so that a round fills the CTA
 static int choose_split(int nblocks, int threads) {
@@ -416,6 +417,7 @@ static int choose_split(int nblocks, int threads) {
 
 struct bsk_cplan {
   int ntri = 0, nrows = 0, nblocks = 0, split = 1, rounds = 1, max_jobs = 1;
+  int max_row[3] = {0, 0, 0};   // largest 4-row block base per triangle slot (bounds the job offsets)
   int sm_count = 148;
   int ncta_alloc = 0;
   int4* d_blocks = nullptr;
@@ -428,15 +430,15 @@ struct bsk_cplan {
   size_t smem_limit = 0;
   std::vector<const void*> last_rowptr;  // what d_rowptr currently holds
   std::vector<int> last_joboff;          // what d_joboff currently holds
-  // tensor-core schedule (contract_tc.cuh); tc_units == 0: list not eligible
-  int tc_units = 0, tc_ncols = 0;
+  // tensor-core schedule (contract_tc.cuh, tc_schedule.h); tc_units == 0: list not eligible
+  int tc_units = 0;
   int path = 0;        // requested: 0 FP32-pipe tile kernel, 1 tensor cores when the call is eligible
   int last_path = 0;   // what the most recent bsk_contract call ran
-  int tc_nu[bsk::tc::NTEAMS] = {0};
-  int tc_col0[bsk::tc::NTEAMS * bsk::tc::UPT] = {0}, tc_ncol[bsk::tc::NTEAMS * bsk::tc::UPT] = {0};
-  uint32_t* d_tc_slots = nullptr;
-  int* d_tc_tri_slot = nullptr;
-  double* d_tc_partial = nullptr;
+  bsk::tcs::Schedule tc_sched;
+  std::vector<int*> d_tc_rawrow;        // per pass
+  std::vector<uint32_t*> d_tc_lanes;    // per pass
+  int64_t* d_tc_tri_slot = nullptr;
+  double* d_tc_partial = nullptr;       // [pass][cta][CAPTOT][128]
 };
 
 using namespace bsk;
@@ -480,173 +482,148 @@ static int contract_impl(bsk_cplan* cp, int64_t ncells, int njobs, double* sums,
   return BSK_OK;
 }
 
-// Tensor-core schedule: every triangle (a <= b <= c after sorting its rows) reads entry
-// D[pair(a,b)][c].  Pair rows are laid out so that the lane that generates a pair already holds
-// one of its two rows in registers ("resident"): lane v of every warp owns row v < 32, and
-// "slot" s = 0..16 pairs it with row (v + s) mod 32, which covers every pair of rows < 32 once;
-// rows >= 32 get one slot each (warp-uniform partner), pairs among rows >= 32 are packed into
-// slots that load both rows.  Four slots (one per TMEM lane quarter) form a 128-row unit.
-// Host part: fills cp->tc_* and the two tables; no CUDA calls (bsk_tc_schedule_info and the CPU
-// tests use it without a device).
-static bool build_tc_schedule_host(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows,
-                                   std::vector<uint32_t>& tab, std::vector<int>& tri_slot) {
+// Tensor-core schedule (tc_schedule.h): upload the per-pass tables.
+static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows) {
   using namespace bsk::tc;
-  if (nrows > MAXR || ntri < 256) return false;
-  const int R = nrows;
-  std::vector<char> need((size_t)R * R, 0);
-  std::vector<int> ta((size_t)ntri), tb((size_t)ntri), tcc((size_t)ntri);
-  for (int t = 0; t < ntri; ++t) {
-    int r[3] = {rows[3 * t], rows[3 * t + 1], rows[3 * t + 2]};
-    std::sort(r, r + 3);
-    ta[t] = r[0]; tb[t] = r[1]; tcc[t] = r[2];
-    need[(size_t)r[0] * R + r[1]] = 1;
+  static_assert(bsk::tcs::kCapTot == CAPTOT && bsk::tcs::kUnits == NUNITS, "schedule / kernel constants");
+  static_assert(bsk::tcs::kTeamCols == TEAMCOLS && bsk::tcs::kMaxUnitCols == MAXCOL, "schedule / kernel constants");
+  if (!bsk::tcs::build_schedule(ntri, rows, nrows, cp->tc_sched)) return false;
+  const auto& sc = cp->tc_sched;
+  for (const auto& ps : sc.passes) {
+    int* d_raw = nullptr;
+    uint32_t* d_lanes = nullptr;
+    if (cudaMalloc((void**)&d_raw, sizeof(int) * ps.rawrow.size()) != cudaSuccess) return false;
+    cp->d_tc_rawrow.push_back(d_raw);
+    if (cudaMemcpy(d_raw, ps.rawrow.data(), sizeof(int) * ps.rawrow.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      return false;
+    if (cudaMalloc((void**)&d_lanes, sizeof(uint32_t) * ps.lane_tab.size()) != cudaSuccess) return false;
+    cp->d_tc_lanes.push_back(d_lanes);
+    if (cudaMemcpy(d_lanes, ps.lane_tab.data(), sizeof(uint32_t) * ps.lane_tab.size(), cudaMemcpyHostToDevice) !=
+        cudaSuccess)
+      return false;
   }
-  struct Slot { uint32_t e[32]; bool used; };
-  const uint32_t idle = (uint32_t)R | ((uint32_t)R << 8);
-  auto fresh = [&](bool resident) { Slot s; for (auto& x : s.e) x = idle | (resident ? 1u << 16 : 0u); s.used = false; return s; };
-  std::vector<Slot> circ(17, fresh(true)), high, loose;
-  std::vector<int> pair_slot((size_t)R * R, -1), pair_lane((size_t)R * R, -1);   // slot ids resolved below
-  // ids: circ s -> s; high b -> 100 + (b - 32); loose k -> 200 + k
-  for (int b = 32; b < R; ++b) high.push_back(fresh(true));
-  int loose_fill = 32;
-  for (int a = 0; a < R; ++a)
-    for (int b = a; b < R; ++b) {
-      if (!need[(size_t)a * R + b]) continue;
-      int sid, lane;
-      uint32_t e;
-      if (b < 32) {
-        const int d = b - a;
-        if (d <= 16) { sid = d; lane = a; e = (uint32_t)a | ((uint32_t)b << 8) | (1u << 16); }
-        else { sid = 32 - d; lane = b; e = (uint32_t)b | ((uint32_t)a << 8) | (1u << 16); }
-        circ[sid].e[lane] = e; circ[sid].used = true;
-      } else if (a < 32) {
-        sid = 100 + (b - 32); lane = a;
-        high[b - 32].e[lane] = (uint32_t)a | ((uint32_t)b << 8) | (1u << 16); high[b - 32].used = true;
-      } else {
-        if (loose_fill == 32) { loose.push_back(fresh(false)); loose_fill = 0; }
-        sid = 200 + (int)loose.size() - 1; lane = loose_fill++;
-        loose.back().e[lane] = (uint32_t)a | ((uint32_t)b << 8); loose.back().used = true;
-      }
-      pair_slot[(size_t)a * R + b] = sid;
-      pair_lane[(size_t)a * R + b] = lane;
-    }
-  // column range [cmin, cmax] each slot needs, from the triangles that read it
-  std::unordered_map<int, std::pair<int, int>> range;
-  for (int t = 0; t < ntri; ++t) {
-    const int sid = pair_slot[(size_t)ta[t] * R + tb[t]];
-    auto it = range.find(sid);
-    if (it == range.end()) range[sid] = {tcc[t], tcc[t]};
-    else { it->second.first = std::min(it->second.first, tcc[t]); it->second.second = std::max(it->second.second, tcc[t]); }
-  }
-  struct SlotRef { int sid; const Slot* s; int cmin, cmax; };
-  std::vector<SlotRef> order;
-  for (int s = 0; s < 17; ++s) if (circ[s].used) order.push_back({s, &circ[s], range[s].first, range[s].second});
-  for (size_t k = 0; k < high.size(); ++k) if (high[k].used) order.push_back({100 + (int)k, &high[k], range[100 + (int)k].first, range[100 + (int)k].second});
-  for (size_t k = 0; k < loose.size(); ++k) order.push_back({200 + (int)k, &loose[k], range[200 + (int)k].first, range[200 + (int)k].second});
-  std::stable_sort(order.begin(), order.end(), [](const SlotRef& x, const SlotRef& y) { return x.cmin / 8 < y.cmin / 8; });
-  const int nunits = ((int)order.size() + 3) / 4;
-  if (nunits < 1 || nunits > NTEAMS * UPT) return false;
-  struct Unit { int first, count, col0, ncol; };
-  std::vector<Unit> units;
-  for (int u = 0; u < nunits; ++u) {
-    Unit un{u * 4, std::min(4, (int)order.size() - u * 4), 1 << 30, 0};
-    int cmax = 0;
-    for (int k = 0; k < un.count; ++k) { un.col0 = std::min(un.col0, order[un.first + k].cmin / 8 * 8); cmax = std::max(cmax, order[un.first + k].cmax); }
-    un.ncol = (cmax + 8) / 8 * 8 - un.col0;
-    units.push_back(un);
-  }
-  // widest units first, dealt alternately to the two teams; position j must fit cap(j)
-  std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.ncol > y.ncol; });
-  const int ncols = (R + 7) / 8 * 8;
-  tab.assign((size_t)NTEAMS * UPT * 128, idle | (1u << 16));
-  for (int t = 0; t < NTEAMS; ++t) cp->tc_nu[t] = 0;
-  std::unordered_map<int, int> slot_pos;   // slot id -> (team * UPT + j) * 4 + q
-  for (int u = 0; u < nunits; ++u) {
-    const int team = u % NTEAMS, j = u / NTEAMS;
-    if (units[u].ncol > cap(j)) return false;
-    cp->tc_nu[team] = j + 1;
-    cp->tc_col0[team * UPT + j] = units[u].col0;
-    cp->tc_ncol[team * UPT + j] = units[u].ncol;
-    for (int k = 0; k < units[u].count; ++k) {
-      const SlotRef& sr = order[units[u].first + k];
-      const int pos = (team * UPT + j) * 4 + k;
-      slot_pos[sr.sid] = pos;
-      for (int l = 0; l < 32; ++l) tab[(size_t)pos * 32 + l] = sr.s->e[l];
-    }
-  }
-  tri_slot.assign((size_t)ntri, 0);
-  for (int t = 0; t < ntri; ++t) {
-    const size_t pi = (size_t)ta[t] * R + tb[t];
-    const int pos = slot_pos[pair_slot[pi]], lane = pair_lane[pi];
-    const int q = pos % 4, tj = pos / 4, team = tj / UPT, j = tj % UPT;
-    tri_slot[t] = ((team * CAPSUM) + capoff(j) + tcc[t] - cp->tc_col0[tj]) * 128 + q * 32 + lane;
-  }
-  cp->tc_units = nunits; cp->tc_ncols = ncols;
+  if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int64_t) * (size_t)ntri) != cudaSuccess) return false;
+  if (cudaMemcpy(cp->d_tc_tri_slot, sc.tri_slot.data(), sizeof(int64_t) * (size_t)ntri, cudaMemcpyHostToDevice) !=
+      cudaSuccess)
+    return false;
+  const size_t slots = (size_t)sc.passes.size() * cp->sm_count * (size_t)sc.pass_stride;
+  if (cudaMalloc((void**)&cp->d_tc_partial, sizeof(double) * slots) != cudaSuccess) return false;
+  cp->tc_units = 0;
+  for (const auto& ps : sc.passes) cp->tc_units += ps.nu[0] + ps.nu[1];
   return true;
 }
 
-static bool build_tc_schedule(bsk_cplan* cp, int ntri, const int32_t* rows, int nrows) {
-  using namespace bsk::tc;
-  std::vector<uint32_t> tab;
-  std::vector<int> tri_slot;
-  if (!build_tc_schedule_host(cp, ntri, rows, nrows, tab, tri_slot)) return false;
-  if (cudaMalloc((void**)&cp->d_tc_slots, sizeof(uint32_t) * tab.size()) != cudaSuccess) return false;
-  cudaMemcpy(cp->d_tc_slots, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice);
-  if (cudaMalloc((void**)&cp->d_tc_tri_slot, sizeof(int) * (size_t)ntri) != cudaSuccess) return false;
-  cudaMemcpy(cp->d_tc_tri_slot, tri_slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice);
-  const size_t stride = (size_t)NTEAMS * CAPSUM * 128;
-  if (cudaMalloc((void**)&cp->d_tc_partial, sizeof(double) * stride * cp->sm_count) != cudaSuccess) return false;
-  return true;
+static void free_tc_schedule(bsk_cplan* cp) {
+  for (int* d : cp->d_tc_rawrow) cudaFree(d);
+  for (uint32_t* d : cp->d_tc_lanes) cudaFree(d);
+  cp->d_tc_rawrow.clear();
+  cp->d_tc_lanes.clear();
+  cudaFree(cp->d_tc_tri_slot);
+  cudaFree(cp->d_tc_partial);
+  cp->d_tc_tri_slot = nullptr;
+  cp->d_tc_partial = nullptr;
+  cp->tc_units = 0;
+}
+
+// fold of the tensor-core partials: tri_slot holds pass * pass_stride + slot; the partials of a
+// pass are laid out [cta][pass_stride]
+__global__ void fold_tc_partials_kernel(const double* __restrict__ partial, int64_t pass_stride, int ncta,
+                                        int ntri, const int64_t* __restrict__ tri_slot,
+                                        double* __restrict__ sums) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntri; t += gridDim.x * blockDim.x) {
+    const int64_t s = tri_slot[t];
+    const int64_t pass = s / pass_stride, slot = s - pass * pass_stride;
+    const double* p = partial + pass * ncta * pass_stride + slot;
+    double acc = 0.0;
+    for (int c = 0; c < ncta; ++c) acc += p[(int64_t)c * pass_stride];
+    sums[t] = acc;
+  }
 }
 
 static int contract_tc_impl(bsk_cplan* cp, int64_t ncells, double* sums, cudaStream_t st) {
   using namespace bsk::tc;
-  Params p;
-  p.rowptr = (const float* const*)cp->d_rowptr;
-  p.nrows = cp->nrows;
-  p.ncols = cp->tc_ncols;
-  p.ntiles = ncells / TL;
-  for (int t = 0; t < NTEAMS; ++t) p.nu[t] = cp->tc_nu[t];
-  p.slot_tab = cp->d_tc_slots;
-  p.partial = cp->d_tc_partial;
-  p.partial_stride = (int64_t)CAPSUM * 128;            // per team; a CTA owns NTEAMS of them
-  for (int i = 0; i < NTEAMS * UPT; ++i) { p.ucol0[i] = cp->tc_col0[i]; p.uncol[i] = cp->tc_ncol[i]; }
-  p.flush_chunks = 512;
-  p.prof = nullptr;
+  const auto& sc = cp->tc_sched;
+  const int64_t ntiles = ncells / TL;
+  const int ncta = (int)std::min<int64_t>(ntiles, cp->sm_count);
+  BSK_CUDA(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+  BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0,
+                           sizeof(double) * sc.passes.size() * (size_t)cp->sm_count * (size_t)sc.pass_stride, st));
+  for (size_t ip = 0; ip < sc.passes.size(); ++ip) {
+    const auto& ps = sc.passes[ip];
+    Params p;
+    p.rowptr = (const float* const*)cp->d_rowptr;
+    p.rawrow = cp->d_tc_rawrow[ip];
+    p.nraw = ps.nraw;
+    p.nbuf = raw_bufs(ps.nraw);
+    p.rawb = raw_bytes(ps.nraw);
+    const int smem_bytes = OFF_RAW + p.nbuf * p.rawb;
+    p.ncols = ps.ncols;
+    for (int i = 0; i < MAXCOL / 8; ++i) p.colslot[i] = ps.colslot[i];
+    p.ntiles = ntiles;
+    for (int t = 0; t < NTEAMS; ++t) p.nu[t] = ps.nu[t];
+    for (int u = 0; u < NUNITS; ++u) { p.ucol0[u] = ps.col0[u]; p.uncol[u] = ps.ncol[u]; p.ublk0[u] = ps.blk0[u]; }
+    p.lane_tab = cp->d_tc_lanes[ip];
+    p.partial = cp->d_tc_partial + ip * (size_t)cp->sm_count * (size_t)sc.pass_stride;
+    p.flush_chunks = 512;
+    p.prof = nullptr;
 #if BSK_TC_PROF
-  static long long* d_prof = nullptr;
-  if (!d_prof) cudaMalloc((void**)&d_prof, 8 * 8 * sizeof(long long));
-  cudaMemsetAsync(d_prof, 0, 8 * 8 * sizeof(long long), st);
-  p.prof = d_prof;
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc((void**)&d_prof, 8 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 8 * 8 * sizeof(long long), st);
+    p.prof = d_prof;
 #endif
-  const int ncta = (int)std::min<int64_t>(p.ntiles, cp->sm_count);
-  BSK_CUDA(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  BSK_CUDA(cudaMemsetAsync(cp->d_tc_partial, 0, sizeof(double) * (size_t)ncta * NTEAMS * p.partial_stride, st));
-  tc_contract_kernel<<<ncta, NTHREADS, SMEM_BYTES, st>>>(p);
-  count_launch();
-  BSK_CUDA(cudaGetLastError());
+    tc_contract_kernel<<<ncta, NTHREADS, smem_bytes, st>>>(p);
+    count_launch();
+    BSK_CUDA(cudaGetLastError());
 #if BSK_TC_PROF
-  {
-    long long h[64];
-    cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
-    for (int t = 0; t < NTEAMS; ++t)
-      fprintf(stderr, "tc prof team %d: units %lld | per unit: raw %.0f gen %.0f a_empty %.0f st+arrive %.0f\n", t, h[t * 8 + 6],
-              (double)h[t * 8] / h[t * 8 + 6], (double)h[t * 8 + 1] / h[t * 8 + 6], (double)h[t * 8 + 2] / h[t * 8 + 6],
-              (double)h[t * 8 + 3] / h[t * 8 + 6]);
-    const long long* m = h + NTEAMS * 8;
-    fprintf(stderr, "tc prof mma: total %lld cycles: a_full %lld d_empty %lld issue %lld b_full %lld\n", m[4], m[0], m[1], m[2], m[3]);
-    for (int t = 0; t < NTEAMS; ++t) {
-      const long long* dr = h + (NTEAMS + 1 + t) * 8;
-      fprintf(stderr, "tc prof drain %d: units %lld | per unit: wait %.0f work %.0f\n", t, dr[2], (double)dr[0] / dr[2], (double)dr[1] / dr[2]);
+    {
+      long long h[64];
+      cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+      for (int t = 0; t < NTEAMS; ++t)
+        fprintf(stderr, "tc prof team %d: units %lld | per unit: raw %.0f gen %.0f a_empty %.0f st+arrive %.0f\n", t, h[t * 8 + 6],
+                (double)h[t * 8] / h[t * 8 + 6], (double)h[t * 8 + 1] / h[t * 8 + 6], (double)h[t * 8 + 2] / h[t * 8 + 6],
+                (double)h[t * 8 + 3] / h[t * 8 + 6]);
+      for (int t = 0; t < NTEAMS; ++t) {
+        const long long* m = h + (NTEAMS + t) * 8;
+        fprintf(stderr, "tc prof mma %d: total %lld cycles: a_full %lld d_empty %lld issue %lld b_full %lld\n", t, m[4], m[0], m[1], m[2], m[3]);
+      }
+      for (int t = 0; t < NTEAMS; ++t) {
+        const long long* dr = h + (2 * NTEAMS + t) * 8;
+        fprintf(stderr, "tc prof drain %d: windows(unit 0) %lld | total: wait %lld work %lld\n", t, dr[2], dr[0], dr[1]);
+      }
     }
-  }
 #endif
-  fold_partials_kernel<<<(int)std::min<int64_t>((cp->ntri + 127) / 128, 148 * 8), 128, 0, st>>>(
-      cp->d_tc_partial, (int64_t)NTEAMS * p.partial_stride, ncta, 1, cp->ntri, 0, cp->d_tc_tri_slot, sums);
+  }
+  fold_tc_partials_kernel<<<(int)std::min<int64_t>((cp->ntri + 127) / 128, 148 * 8), 128, 0, st>>>(
+      cp->d_tc_partial, sc.pass_stride, cp->sm_count, cp->ntri, cp->d_tc_tri_slot, sums);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   return BSK_OK;
 }
+
+static int cplan_alloc(bsk_cplan* cp, const std::vector<int4>& blocks, const std::vector<int>& slot, int ntri,
+                       int nrows, int max_jobs) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  BSK_CUDA(cudaGetDevice(&dev));
+  BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  cp->sm_count = prop.multiProcessorCount;
+  cp->smem_limit = prop.sharedMemPerBlockOptin;
+  cp->ncta_alloc = cp->sm_count;
+  BSK_CUDA(cudaMalloc((void**)&cp->d_blocks, sizeof(int4) * blocks.size()));
+  BSK_CUDA(cudaMemcpy(cp->d_blocks, blocks.data(), sizeof(int4) * blocks.size(), cudaMemcpyHostToDevice));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_tri_slot, sizeof(int) * (size_t)ntri));
+  BSK_CUDA(cudaMemcpy(cp->d_tri_slot, slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_partial,
+                      sizeof(double) * (size_t)cp->ncta_alloc * max_jobs * 64 * cp->nblocks));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_rowptr, sizeof(void*) * (size_t)nrows));
+  BSK_CUDA(cudaMallocHost((void**)&cp->h_rowptr, sizeof(void*) * (size_t)nrows));
+  BSK_CUDA(cudaMalloc((void**)&cp->d_joboff, sizeof(int) * 3 * (size_t)max_jobs));
+  BSK_CUDA(cudaMallocHost((void**)&cp->h_joboff, sizeof(int) * 3 * (size_t)max_jobs));
+  return BSK_OK;
+}
+
+extern "C" int bsk_cplan_destroy(bsk_cplan* cp);
 
 extern "C" {
 
@@ -688,28 +665,21 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
     const uint64_t key = ((uint64_t)(r1 >> 2) << 40) | ((uint64_t)(r2 >> 2) << 20) | (uint64_t)(r3 >> 2);
     slot[t] = slot[t] * cp->nblocks + index[key];
   }
+  for (const int4& b : blocks) {
+    cp->max_row[0] = std::max(cp->max_row[0], b.x);
+    cp->max_row[1] = std::max(cp->max_row[1], b.y);
+    cp->max_row[2] = std::max(cp->max_row[2], b.z);
+  }
   const int best = choose_split(cp->nblocks, kThreads);
   cp->split = best;
   cp->rounds = (cp->nblocks * best + kThreads - 1) / kThreads;
-
-  int dev = 0;
-  cudaDeviceProp prop;
-  BSK_CUDA(cudaGetDevice(&dev));
-  BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
-  cp->sm_count = prop.multiProcessorCount;
-  cp->smem_limit = prop.sharedMemPerBlockOptin;
-  cp->ncta_alloc = cp->sm_count;
-  BSK_CUDA(cudaMalloc((void**)&cp->d_blocks, sizeof(int4) * blocks.size()));
-  BSK_CUDA(cudaMemcpy(cp->d_blocks, blocks.data(), sizeof(int4) * blocks.size(), cudaMemcpyHostToDevice));
-  BSK_CUDA(cudaMalloc((void**)&cp->d_tri_slot, sizeof(int) * (size_t)ntri));
-  BSK_CUDA(cudaMemcpy(cp->d_tri_slot, slot.data(), sizeof(int) * (size_t)ntri, cudaMemcpyHostToDevice));
-  BSK_CUDA(cudaMalloc((void**)&cp->d_partial,
-                      sizeof(double) * (size_t)cp->ncta_alloc * max_jobs * 64 * cp->nblocks));
-  BSK_CUDA(cudaMalloc((void**)&cp->d_rowptr, sizeof(void*) * (size_t)nrows));
-  BSK_CUDA(cudaMallocHost((void**)&cp->h_rowptr, sizeof(void*) * (size_t)nrows));
-  BSK_CUDA(cudaMalloc((void**)&cp->d_joboff, sizeof(int) * 3 * (size_t)max_jobs));
-  BSK_CUDA(cudaMallocHost((void**)&cp->h_joboff, sizeof(int) * 3 * (size_t)max_jobs));
-  if (!build_tc_schedule(cp, ntri, rows, nrows)) cp->tc_units = 0;
+  // any failure below releases what was allocated so far (bsk_cplan_destroy copes with nulls)
+  const int rc = cplan_alloc(cp, blocks, slot, ntri, nrows, max_jobs);
+  if (rc != BSK_OK) {
+    bsk_cplan_destroy(cp);
+    return rc;
+  }
+  if (!build_tc_schedule(cp, ntri, rows, nrows)) free_tc_schedule(cp);
   *out = cp;
   return BSK_OK;
 }
@@ -723,9 +693,7 @@ int bsk_cplan_destroy(bsk_cplan* cp) {
   cudaFreeHost(cp->h_rowptr);
   cudaFree(cp->d_joboff);
   cudaFreeHost(cp->h_joboff);
-  cudaFree(cp->d_tc_slots);
-  cudaFree(cp->d_tc_tri_slot);
-  cudaFree(cp->d_tc_partial);
+  free_tc_schedule(cp);
   delete cp;
   return BSK_OK;
 }
@@ -744,26 +712,36 @@ int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6
   BSK_REQUIRE(rows && out && ntri > 0 && nrows > 0, "bsk_tc_schedule_info: bad argument");
   for (int i = 0; i < 3 * ntri; ++i)
     BSK_REQUIRE(rows[i] >= 0 && rows[i] < nrows, "bsk_tc_schedule_info: row index %d outside [0,%d)", rows[i], nrows);
-  bsk_cplan tmp;
-  std::vector<uint32_t> tab;
-  std::vector<int> tri_slot;
   for (int i = 0; i < 6; ++i) out[i] = 0;
-  if (!build_tc_schedule_host(&tmp, ntri, rows, nrows, tab, tri_slot)) return BSK_OK;   // not eligible
-  std::vector<int> sorted(tri_slot);
-  std::sort(sorted.begin(), sorted.end());
-  int64_t distinct = sorted.empty() ? 0 : 1;
-  for (size_t i = 1; i < sorted.size(); ++i) distinct += sorted[i] != sorted[i - 1];
-  int64_t cols = 0, pair_rows = 0, in_range = 1;
-  for (int i = 0; i < NTEAMS * UPT; ++i) cols += tmp.tc_ncol[i];
-  const uint32_t idle = (uint32_t)nrows | ((uint32_t)nrows << 8);
-  for (uint32_t e : tab) pair_rows += (e & 0xFFFFu) != idle;
-  for (int t = 0; t < ntri; ++t) in_range &= tri_slot[t] >= 0 && tri_slot[t] < NTEAMS * CAPSUM * 128;
-  out[0] = tmp.tc_units;      // 128-row units
-  out[1] = distinct;          // distinct accumulator slots the triangles read (== ntri when injective)
-  out[2] = cols;              // sum over units of the accumulator columns (MMA cost ~ 128 * cols)
-  out[3] = pair_rows;         // pair rows generated (<= 128 * units)
+  bsk::tcs::Schedule sc;
+  if (!bsk::tcs::build_schedule(ntri, rows, nrows, sc)) return BSK_OK;   // not eligible
+  // distinct (sorted triangle -> slot) pairs: different sorted triangles must read different slots
+  std::vector<std::pair<int64_t, int64_t>> key((size_t)ntri);
+  for (int t = 0; t < ntri; ++t) {
+    int64_t r[3] = {rows[3 * t], rows[3 * t + 1], rows[3 * t + 2]};
+    std::sort(r, r + 3);
+    key[t] = {sc.tri_slot[t], (r[0] * nrows + r[1]) * nrows + r[2]};
+  }
+  std::sort(key.begin(), key.end());
+  int64_t distinct_slots = 0, distinct_tris = 0, in_range = 1;
+  for (size_t i = 0; i < key.size(); ++i) {
+    distinct_slots += i == 0 || key[i].first != key[i - 1].first;
+    distinct_tris += i == 0 || key[i] != key[i - 1];
+  }
+  int64_t units = 0, cols = 0, cost = 0;
+  for (const auto& ps : sc.passes) {
+    units += ps.nu[0] + ps.nu[1];
+    for (int u = 0; u < NUNITS; ++u) cols += ps.ncol[u];
+    cost += ps.mma_cost;
+  }
+  const int64_t total_slots = (int64_t)sc.passes.size() * sc.pass_stride;
+  for (int t = 0; t < ntri; ++t) in_range &= sc.tri_slot[t] >= 0 && sc.tri_slot[t] < total_slots;
+  out[0] = units;                                        // 128-row units over all passes
+  out[1] = distinct_slots == distinct_tris ? distinct_slots : -distinct_slots;   // injective: == distinct sorted triangles
+  out[2] = cols;                                         // sum over units of the accumulator columns
+  out[3] = (int64_t)sc.passes.size();                    // launches (passes)
   out[4] = in_range;
-  out[5] = (int64_t)NTEAMS * CAPSUM * 128;
+  out[5] = cost;                                         // sum over units of max(11, ncol/2)
   return BSK_OK;
 }
 
@@ -802,8 +780,8 @@ int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int 
   for (int j = 0; j < njobs; ++j)
     for (int k = 0; k < 3; ++k) {
       const int off = job_off[3 * j + k];
-      BSK_REQUIRE(off >= 0 && off % 4 == 0 && off < cp->nrows,
-                  "bsk_contract: job offset %d must be a multiple of 4 inside the row set", off);
+      BSK_REQUIRE(off >= 0 && off % 4 == 0 && off + cp->max_row[k] + 4 <= cp->nrows,
+                  "bsk_contract: job offset %d must be a multiple of 4 and keep every 4-row block inside the row set", off);
       jo[3 * j + k] = off;
     }
   if (rp != cp->last_rowptr || jo != cp->last_joboff) {
@@ -869,8 +847,8 @@ int bsk_reduce_list(const void* const* row_ptrs, int nrows, int precision, int64
   count_launch();
   BSK_CUDA(cudaGetLastError());
   BSK_CUDA(cudaFreeAsync(d, st));
-  // the host tables may be reused by the caller as soon as we return
-  BSK_CUDA(cudaStreamSynchronize(st));
+  // row_ptrs / rows are pageable host memory: cudaMemcpyAsync has staged them before it returned,
+  // so the caller may reuse them now and no stream synchronisation is needed
   return BSK_OK;
 }
 

@@ -1,33 +1,47 @@
 // Tensor-core triangle contraction (sm_100a, tcgen05 + TMEM), included by contract.cu.
 //
-//   D[(a,b), c] = sum_x (F_a(x) F_b(x)) * F_c(x)        for every row pair (a,b) and every row c
+//   D[(a,b), c] = sum_x (F_a(x) F_b(x)) * F_c(x)        for row pairs (a,b) and rows c
 //
 // i.e. the reference's T separate np.sum(f[a]*f[b]*f[c]) loops (bskit/main.py:1871-1879) recast
-// as one skinny GEMM over the grid axis: M = row pairs (128 per "unit"), N = rows (<= 40),
-// K = cells.  Measured on B200 (profiles/r1_tcgen05_probe.txt): with M = 128 a tcgen05.mma costs
-// 128*N/256 cycles only when the A operand comes from TMEM (44 instead of 24 cycles at N = 48
-// from shared memory), so the pair products -- which have to be generated on the CUDA cores
-// anyway -- are written straight into TMEM and never touch shared memory.
+// as a skinny GEMM over the grid axis: M = row pairs (128 per "unit"), N = the rows c the unit's
+// triangles need, K = cells.  Measured on B200 (profiles/r1_tcgen05_probe.txt): with M = 128 a
+// tcgen05.mma costs max(~11, 128*N/256) cycles only when the A operand comes from TMEM, so the
+// pair products -- generated on the CUDA cores anyway -- are written straight to TMEM with
+// tcgen05.st and never touch shared memory; B = the fields, converted once per tile into K-major
+// core matrices (hi and lo images).
+//
+// What bounds the kernel is shared-memory bandwidth: every pair row needs the cells of its two
+// fields in the registers of the lane that owns the row.  Round 1 read both rows per lane and
+// unit (8 wavefronts per 4 cells and warp).  Measured (scripts/dev/lds_probe.cu,
+// profiles/r2_lds_probe.txt): a warp-wide LDS.128 costs 4 cycles when the lanes read 32 different
+// 16-byte chunks, 2 cycles when every even/odd lane pair reads the same chunk.  The layout here:
+//   * rows are handled in groups of 8; a generator warp "hosts" one group for the whole chunk:
+//     lane l keeps row 8*host + (l & 7) of the chunk in registers (32 cells) across the units;
+//   * in unit j the warp meets a partner group: lane pair k = l >> 1 reads row
+//     8*part + ((k & 7) + s) & 7, s = 2*piece + (k >> 3) -- lane pairs share the chunk they read
+//     (2-cycle LDS), the 8 pairs of a half warp read 8 consecutive rows (distinct banks), and
+//     two such "pieces" cover all 64 pairs of two groups.
+// Shared-memory reads per 4 cells, warp and unit drop from 8 wavefronts to 2 (+ 4/U for the
+// resident row, U = units that share the host group).
 //
 // Numerics.  3xTF32: P = F_a*F_b (fp32, RN) is split P = P_hi + P_lo, F_c = C_hi + C_lo with
-// 11-bit pieces (hi parts rounded to nearest), and D += P_lo*C_hi + P_hi*C_lo + P_hi*C_hi.  The
-// tensor core truncates its fp32 accumulator (round toward zero,
-// profiles/r1_tensor_core_rounding_probe.txt), which biases a long heavily-cancelling sum
-// (~3.5e-7 per 32 cells accumulated), so an accumulator lives in TMEM for one window of WIN
-// chunks only; it is then drained into fp32 registers with round-to-nearest adds, and those are
-// flushed into float64 partials every few hundred chunks.  TMEM reads run at 64 B/cycle/SM, so
-// the window is a speed/bias trade (WIN = 1 / 2 / 4: 70.7 / 52.3 / 47.6 ms, 3.7e-7 / 6.0e-7 /
-// 9.2e-7 of max|sum| at 512^3, S = 40; FP32-pipe kernel: 71 ms, 5e-8).
+// 11-bit pieces (hi parts rounded to nearest), D += P_lo*C_hi + P_hi*C_lo + P_hi*C_hi.  The
+// tensor core truncates its fp32 accumulator (profiles/r1_tensor_core_rounding_probe.txt), so an
+// accumulator lives in TMEM for one window of WIN chunks only; it is then drained into fp32
+// registers (round-to-nearest adds), flushed into float64 partials every flush_chunks chunks.
+// Window ends are staggered over the units so the TMEM reads (64 B/cycle/SM) spread evenly.
 //
-// Roles (640 threads, one CTA per SM, persistent over tiles of 128 cells; setmaxnreg 72/144/40):
-//   2 x 4 warps      generator teams, pure producers: warp q of a team owns TMEM lanes
-//                    [32q, 32q+32) and writes the hi / lo pair products of one unit (128 pair rows x
-//                    32 cells) into one of the team's two A buffers
-//   2 x 4 warps      drain warpgroups, one per team: own the second-level accumulators
-//   1 warp           TMA producer: raw [row][cell] tiles, cp.async.bulk + mbarrier
-//   1 warp           MMA issuer (one elected lane): 12 MMAs per unit into the unit's own accumulator
-//   2 warps          convert the raw tile to the B operand images (hi / lo, K-major core
-//                    matrices: 8 rows x 16 bytes)
+// Roles (640 threads, one CTA per SM, persistent over tiles of 128 cells; setmaxnreg 96/120/40):
+//   2 x 4 warps  generator teams: warp q of a team owns TMEM lanes [32q, 32q+32)
+//   2 x 4 warps  drain warpgroups, one per team: second-level accumulators of the team's units
+//                (96 columns per team, handed out to the units in blocks of 8)
+//   1 warp       TMA producer (raw [row][cell] tiles, cp.async.bulk + mbarrier), up to 3 tiles ahead
+//   2 warps      MMA issuers, one per team (one elected lane each)
+//   (the generators also convert the raw tile into the operand images at the start of a tile)
+//
+// A launch processes one "pass": <= 8 units with <= 96 accumulator columns per team, over a
+// window of <= 40 column rows and <= MAXRAW raw rows.  Lists that need more (S = 80 bins, 2-3
+// field cross lists) run as several passes (host schedule: contract.cu, build_tc_schedule_host).
 #pragma once
 
 namespace bsk {
@@ -36,52 +50,52 @@ namespace tc {
 constexpr int CH = 32;            // cells per chunk = K extent of one unit
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
-constexpr int WIN = 4;            // chunks accumulated in TMEM before a drain (divides NCH): the
-                                  // accumulator truncates, so the window bounds the bias (~3.5e-7 per chunk)
-static_assert(NCH % WIN == 0, "window");
-constexpr int MAXR = 40;          // rows (N <= 40)
+constexpr int WIN = 4;            // chunks accumulated in TMEM before a drain
+constexpr int MAXCOL = 40;        // column rows per pass (N of an MMA <= 40)
+constexpr int MAXRAW = 120;       // raw rows per pass (8-row groups: 15)
 constexpr int NTEAMS = 2;
-constexpr int UPT = 4;            // units per team (NTEAMS * UPT * 128 pair rows at most)
-constexpr int NTEAMTHREADS = NTEAMS * 128;
-constexpr int NTHREADS = 2 * NTEAMTHREADS + 128;    // generator teams + one drain warpgroup per team + 4 auxiliary warps
+constexpr int UPT = 4;            // units per team
+constexpr int NUNITS = NTEAMS * UPT;
+constexpr int NGEN = NTEAMS * 128;
+constexpr int NTHREADS = 2 * NGEN + 128;    // generator teams + one drain warpgroup per team + 4 auxiliary warps
 #ifndef BSK_TC_PROF
 #define BSK_TC_PROF 0
 #endif
 constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
 // 640 threads are launched with 96 registers each; setmaxnreg then moves registers from the
-// generator and auxiliary warpgroups to the drain warpgroups, which hold the second-level
-// accumulators: 256*72 + 256*144 + 128*40 <= 640*96
-constexpr int REGS_TEAM = 72, REGS_DRAIN = 144, REGS_AUX = 40;
-constexpr bool USE_OWN = false;   // lane v keeps row v of the chunk in registers across its team's units
-static_assert(NTEAMTHREADS * (REGS_TEAM + REGS_DRAIN) + 128 * REGS_AUX <= NTHREADS * (65536 / NTHREADS / 8 * 8), "register split");
-static_assert(NTEAMTHREADS * (96 - REGS_TEAM) + 128 * (96 - REGS_AUX) >= NTEAMTHREADS * (REGS_DRAIN - 96), "setmaxnreg pool");
-// D columns a unit may need, by its position j in the team (units are sorted by decreasing width
-// and dealt round-robin to the teams): a pair (a <= b) only meets rows c >= b, so most units need
-// few columns
-__host__ __device__ constexpr int cap(int j) { return j == 0 ? 40 : j == 1 ? 32 : j == 2 ? 24 : 8; }
-__host__ __device__ constexpr int capoff(int j) { return j == 0 ? 0 : j == 1 ? 40 : j == 2 ? 72 : 96; }
-constexpr int CAPSUM = 104;       // per team
-// TMEM columns: one accumulator per unit (cap(j) columns) and two A buffers (hi 32 + lo 32
-// columns) per team
+// auxiliary warps to the drain warpgroups, which hold the second-level accumulators
+constexpr int REGS_GEN = 96, REGS_DRAIN = 120, REGS_AUX = 40;
+static_assert(NGEN * (REGS_GEN + REGS_DRAIN) + 128 * REGS_AUX <= NTHREADS * 96, "register split");
+// accumulator columns per team: 12 blocks of 8 columns, handed out to the team's units by the
+// host (Params::ublk0); a unit of width ncol uses ncol/8 consecutive blocks
+constexpr int TEAMCOLS = 96, NBLK = TEAMCOLS / 8;
+constexpr int CAPTOT = NTEAMS * TEAMCOLS;   // 192
+// TMEM columns: the teams' accumulators and two A buffers (hi 32 + lo 32 columns) per team
 constexpr int TM_D = 0, TM_A = 256;
-static_assert(NTEAMS * CAPSUM <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
+static_assert(CAPTOT <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
 
-constexpr int RAW_STRIDE = TL * 4 + 16;            // bytes; +16 keeps lanes on distinct banks
-constexpr int RAW_BYTES = ((MAXR + 1) * RAW_STRIDE + 127) / 128 * 128;  // + one all-zero row for idle lanes
-constexpr int BIMG_BYTES = (TL / 4) * (MAXR / 8) * 128;   // one hi or lo image of a tile
+constexpr int RAW_STRIDE = TL * 4 + 16;            // bytes; 8 consecutive rows tile the 32 banks
+constexpr int MAXRAWBUF = 4;                       // raw tiles in flight (as many as fit next to the images)
+constexpr int BIMG_BYTES = (TL / 4) * (MAXCOL / 8) * 128;   // one hi or lo image of a tile
 constexpr int OFF_BAR = 0;
-constexpr int OFF_RAW = 512;
-constexpr int OFF_BIMG = OFF_RAW + 2 * RAW_BYTES;  // [buf][hi|lo]
-constexpr int SMEM_BYTES = OFF_BIMG + 4 * BIMG_BYTES;
-static_assert(OFF_BIMG % 128 == 0, "operand images must be 128-byte aligned");
+constexpr int OFF_BIMG = 512;                      // [buf][hi|lo]
+constexpr int OFF_RAW = OFF_BIMG + 4 * BIMG_BYTES;
+constexpr int SMEM_MAX = 227 * 1024;
+static_assert(OFF_BIMG % 128 == 0 && OFF_RAW % 128 == 0, "operand images must be 128-byte aligned");
+// bytes of one raw buffer: nraw rows + one all-zero row
+__host__ __device__ constexpr int raw_bytes(int nraw) { return ((nraw + 1) * RAW_STRIDE + 127) / 128 * 128; }
+__host__ __device__ constexpr int raw_bufs(int nraw) {
+  return (SMEM_MAX - OFF_RAW) / raw_bytes(nraw) < MAXRAWBUF ? (SMEM_MAX - OFF_RAW) / raw_bytes(nraw) : MAXRAWBUF;
+}
+static_assert(raw_bufs(MAXRAW) >= 2, "shared memory");
 
 // barrier indices
 enum {
-  RAW_FULL = 0, RAW_EMPTY = 2, B_FULL = 4, B_EMPTY = 6,
-  A_FULL = 8, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NTEAMS * UPT,
-  NBAR = D_EMPTY + NTEAMS * UPT
+  RAW_FULL = 0, RAW_EMPTY = RAW_FULL + MAXRAWBUF, B_FULL = RAW_EMPTY + MAXRAWBUF, B_EMPTY = B_FULL + 2,
+  A_FULL = B_EMPTY + 2, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NUNITS,
+  NBAR = D_EMPTY + NUNITS
 };
-static_assert(NBAR * 8 + 8 <= OFF_RAW, "barrier area");
+static_assert(NBAR * 8 + 8 <= OFF_BIMG, "barrier area");
 
 // bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void tc_wait(uint32_t bar_addr, uint32_t parity) {
@@ -117,16 +131,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc)
-               : "memory");
-}
-template <int ACC>
-__device__ __forceinline__ void mma_tf32_ts2(uint32_t d, uint32_t a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
-  asm volatile("{\n.reg .b64 bd;\nmov.b64 bd, {%2, %3};\n"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, %5;\n}\n" ::"r"(d), "r"(a), "r"(desc_lo), "r"(desc_hi),
-               "r"(idesc), "n"(ACC)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n}\n" ::"r"(d), "r"(a), "r"(desc_lo), "r"(desc_hi),
+               "r"(idesc), "r"(acc)
                : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
@@ -155,114 +164,219 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// L2 policies: the fields stream through once per pass (evict first), the float64 partials are
+// re-read by every flush (evict last) -- keeps the flushes out of DRAM
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+// float -> double conversion inside the asm statement: left to the compiler, the conversions of
+// all accumulators are hoisted in front of the reductions and double the register demand
+__device__ __forceinline__ void red_add_f64_hint(double* addr, float v, uint64_t pol) {
+  asm volatile("{\n.reg .f64 d;\ncvt.f64.f32 d, %1;\nred.global.add.L2::cache_hint.f64 [%0], d, %2;\n}\n" ::"l"(addr), "f"(v), "l"(pol)
+               : "memory");
+}
 
 struct Params {
-  const float* const* rowptr;
-  int nrows;        // R <= 40
-  int ncols;        // N = R rounded up to 8
-  int64_t ntiles;   // ncells / TL
-  int nu[NTEAMS];             // units per team
-  int ucol0[NTEAMS * UPT];    // [team * UPT + j]: first D column the unit needs (multiple of 8)
-  int uncol[NTEAMS * UPT];    //                   number of columns (multiple of 8, <= cap(j))
-  const uint32_t* slot_tab;   // [team * UPT + j][4][32]: ra | rb << 8  (row index R = zero row)
-  double* partial;            // [cta][team][CAPSUM][128]
-  int64_t partial_stride;
+  const float* const* rowptr;   // field-table rows (device pointers)
+  const int* rawrow;            // [nraw]: field-table row loaded into raw slot s, -1: the slot stays zero
+  int nraw;                     // raw slots (multiple of 8, <= MAXRAW); slot nraw is the zero row
+  int nbuf, rawb;               // raw tiles in flight (2..4) and bytes per raw buffer
+  int ncols;                    // column rows of the window (multiple of 8, <= MAXCOL)
+  int colslot[MAXCOL / 8];      // raw slot of the first row of each 8-column block
+  int64_t ntiles;               // ncells / TL
+  int nu[NTEAMS];               // units per team
+  int ucol0[NUNITS];            // [team * UPT + j]: first D column the unit needs (multiple of 8)
+  int uncol[NUNITS];            //                   number of columns (multiple of 8)
+  int ublk0[NUNITS];            //                   first accumulator block of the unit within its team
+  const uint32_t* lane_tab;     // [team * UPT + j][128]: a_slot | b_slot << 8
+  double* partial;              // [cta][team][TEAMCOLS][128]
   int flush_chunks;
-  long long* prof;            // PROF only: [team warp q=0: 8 counters per team][mma: 8 counters]
+  long long* prof;              // PROF only
 };
 
-// Generator team member; q = warp % 4 is the TMEM lane quarter.  Pure producer: waits for a
-// free A buffer, writes the 128 x 32 pair products (hi, lo) of one unit, signals the MMA issuer.
+// window bookkeeping shared by the MMA issuers and the drain warps: unit u closes its window
+// after chunk g (running count over this CTA's chunks) when (g + u) % WIN == WIN - 1 or g is
+// the last chunk
+__device__ __forceinline__ bool win_closes(uint32_t g, int u, uint32_t gtot) {
+  return ((g + (uint32_t)u) % WIN) == WIN - 1 || g + 1 == gtot;
+}
+__device__ __forceinline__ bool win_opens(uint32_t g, int u) { return g == 0 || ((g + (uint32_t)u) % WIN) == 0; }
+
+// operand-image conversion, done by the 256 generator threads at the start of a tile (a separate
+// converter warp pair could not keep up once the generators got faster): raw fp32 -> tf32 hi
+// (round to nearest) + lo.  Thread gt owns column gt & 63 (if it exists) and the 4-cell groups
+// g = (gt >> 6) + 4k: 8 independent items per thread, 5 % of a tile's generator instructions.
+__device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uint32_t img_hi, uint32_t img_lo, int gt,
+                                              uint32_t col_slot) {
+  const int l = gt & 63;
+  if (l < p.ncols) {
+    const uint32_t ngrp = (uint32_t)(p.ncols / 8) * 128u;
+    const uint32_t row = raw + col_slot * RAW_STRIDE;
+    const uint32_t o = (uint32_t)(l >> 3) * 128u + (uint32_t)(l & 7) * 16u;
+#pragma unroll
+    for (int k = 0; k < TL / 16; ++k) {
+      const uint32_t g = (uint32_t)(gt >> 6) + 4u * k;
+      const float4 v = lds128(row + g * 16u);
+      const float x[4] = {v.x, v.y, v.z, v.w};
+      uint32_t h[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = (__float_as_uint(x[e]) + 0x1000u) & 0xFFFFE000u;
+        lo[e] = __float_as_uint(x[e] - __uint_as_float(h[e]));
+      }
+      sts128(img_hi + g * ngrp + o, h[0], h[1], h[2], h[3]);
+      sts128(img_lo + g * ngrp + o, lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Generator team member; q = warp % 4 is the TMEM lane quarter.  Pure producer: writes the
+// 128 x 32 pair products (hi, lo) of one unit into one of the team's two A buffers.  The
+// hand-over of a unit (tcgen05.wait::st + arrive) is deferred until the first products of the next
+// unit are in registers, and the A buffer is probed (test_wait) before the loads are issued, so
+// neither latency is exposed; a warp without a piece in a unit only keeps the protocol going.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  return ok;
+}
 __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase,
                                           int team, int q, int lane) {
   const int my_nu = p.nu[team];
-  const int R = p.nrows;
   uint32_t rb_off[UPT], ra_off[UPT];
-  bool resident[UPT];   // warp-uniform: every lane's first row is row `lane` (or the lane is idle)
+  bool reload[UPT];     // warp-uniform: the resident row changes with this unit
+  bool idle[UPT];       // warp-uniform: this warp has no piece in the unit
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
-    uint32_t e = (uint32_t)R | ((uint32_t)R << 8) | (1u << 16);
-    if (j < my_nu) e = p.slot_tab[((team * UPT + j) * 4 + q) * 32 + lane];
+    const uint32_t none = (uint32_t)p.nraw | ((uint32_t)p.nraw << 8);
+    uint32_t e = none;
+    if (j < my_nu) e = p.lane_tab[((team * UPT + j) * 4 + q) * 32 + lane];
     ra_off[j] = (e & 0xFFu) * RAW_STRIDE;
     rb_off[j] = ((e >> 8) & 0xFFu) * RAW_STRIDE;
-    resident[j] = USE_OWN && __all_sync(0xffffffffu, (e >> 16) & 1u);
+    idle[j] = __all_sync(0xffffffffu, e == none);
+    reload[j] = j == 0 || __any_sync(0xffffffffu, ra_off[j] != ra_off[j - 1]);
   }
-  const uint32_t own_off = (uint32_t)(lane < R ? lane : R) * RAW_STRIDE;
+  // the resident row must be (re)loaded in the first non-idle unit of a chunk
+  {
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) {
+      if (idle[j]) continue;
+      if (!have) reload[j] = true;
+      have = true;
+    }
+  }
+  const int gt = team * 128 + q * 32 + lane;
+  const uint32_t col_slot = (gt & 63) < p.ncols ? (uint32_t)(p.colslot[(gt & 63) >> 3] + (gt & 7)) : 0u;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
   const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
   uint32_t n_gen = 0;     // units generated by this team so far
+  bool pending = false;   // the previous unit's stores have not been handed over yet
+  uint32_t pending_ab = 0;
   long long t_raw = 0, t_gen = 0, t_aempty = 0, t_st = 0, t_mark = 0;
   auto tick = [&](long long& acc_t) {
     if constexpr (PROF) { const long long now = clock64(); acc_t += now - t_mark; t_mark = now; }
+  };
+  auto hand_over = [&]() {
+    if (pending) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull + pending_ab * 8);
+      pending = false;
+    }
   };
   if constexpr (PROF) t_mark = clock64();
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
+    const int buf = it % p.nbuf;
+    tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it / p.nbuf) & 1u);
     tick(t_raw);
-    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * RAW_BYTES);
+    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb);
+    {   // this thread's share of the tile's operand images (the MMAs of tile it-2 have released them)
+      const int bbuf = it & 1;
+      tc_wait(bars + (B_EMPTY + bbuf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      convert_share(p, raw, smem_u32(smem + OFF_BIMG + (bbuf * 2 + 0) * BIMG_BYTES),
+                    smem_u32(smem + OFF_BIMG + (bbuf * 2 + 1) * BIMG_BYTES), gt, col_slot);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + (B_FULL + bbuf) * 8);
+      tick(t_raw);
+    }
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       const uint32_t cbase = raw + c * (CH * 4);
       float4 own[CH / 4];
-      if constexpr (USE_OWN) {
-#pragma unroll
-        for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + own_off + v4 * 16);
-      }
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j < my_nu) {
           const uint32_t ab = n_gen & 1u;
           const uint32_t a_tmem = a_tmem0 + ab * 64u;
-          bool waited = false;
+          const uint32_t ok = mbar_test(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
+          if (idle[j]) {
+            hand_over();
+            if (!ok) tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
+          } else {
+            if (reload[j]) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {   // 8 cells at a time
-            const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
-            float4 a0, a1;
-            if (USE_OWN && resident[j]) {
-              a0 = own[2 * h];
-              a1 = own[2 * h + 1];
-            } else {
-              a0 = lds128(cbase + ra_off[j] + h * 32);
-              a1 = lds128(cbase + ra_off[j] + h * 32 + 16);
+              for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + ra_off[j] + v4 * 16);
             }
-            const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-            const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 pr = __fmul2_rn(pa[i], pb[i]);
-              // hi = product rounded to nearest tf32 (11 bits): the low part is then sign-symmetric and
-              // at most 2^-12 |P|, so the tensor core's truncation of it costs 2^-23 instead of 2^-22
-              const float2 ph = make_float2(__uint_as_float((__float_as_uint(pr.x) + 0x1000u) & 0xFFFFE000u),
-                                            __uint_as_float((__float_as_uint(pr.y) + 0x1000u) & 0xFFFFE000u));
-              const float2 pl = __ffma2_rn(ph, make_float2(-1.f, -1.f), pr);   // exact
-              hi[2 * i] = __float_as_uint(ph.x); hi[2 * i + 1] = __float_as_uint(ph.y);
-              lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);
+            for (int h = 0; h < 4; ++h) {   // 8 cells at a time
+              const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
+              const float4 a0 = own[2 * h], a1 = own[2 * h + 1];
+              const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+              const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 pr = __fmul2_rn(pa[i], pb[i]);
+                // hi = product rounded to nearest tf32 (11 bits): the low part is then sign-symmetric and
+                // at most 2^-12 |P|, so the tensor core's truncation of it costs 2^-23 instead of 2^-22
+                const float2 ph = make_float2(__uint_as_float((__float_as_uint(pr.x) + 0x1000u) & 0xFFFFE000u),
+                                              __uint_as_float((__float_as_uint(pr.y) + 0x1000u) & 0xFFFFE000u));
+                const float2 pl = __ffma2_rn(ph, make_float2(-1.f, -1.f), pr);   // exact
+                hi[2 * i] = __float_as_uint(ph.x); hi[2 * i + 1] = __float_as_uint(ph.y);
+                lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);
+              }
+              if (h == 0) {
+                tick(t_gen);
+                hand_over();          // the previous unit: its stores have long landed
+                tick(t_st);
+                if (!ok) tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                tick(t_aempty);
+              }
+              tmem_st8(a_tmem + h * 8, hi);
+              tmem_st8(a_tmem + 32 + h * 8, lo);
             }
-            if (!waited) {
-              tick(t_gen);
-              tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
-              tc_fence_after();
-              waited = true;
-              tick(t_aempty);
-            }
-            tmem_st8(a_tmem + h * 8, hi);
-            tmem_st8(a_tmem + 32 + h * 8, lo);
+            tick(t_gen);
           }
-          tick(t_gen);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_afull + ab * 8);
+          pending = true;
+          pending_ab = ab;
           ++n_gen;
-          tick(t_st);
         }
       }
     }
+    hand_over();     // before the raw buffer is released and a (possibly long) wait for the next tile
+    tick(t_st);
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
   }
@@ -274,11 +388,25 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
   }
 }
 
-// Drain warp (team, q): after each of its team's units has had its 12 MMAs, adds the accumulator of
-// TMEM lanes [32q, 32q+32) into fp32 registers (round to nearest) and releases the accumulator;
-// flushes to the float64 partials every flush_chunks chunks.
-template <int J>
-__device__ __forceinline__ void drain_unit(float2 (&acc)[cap(J) / 2], int ncol, uint32_t d_tmem, uint32_t bar_full,
+// Drain warp (team, q): after a unit's window has had its MMAs, adds the accumulator of TMEM
+// lanes [32q, 32q+32) into fp32 registers (round to nearest) and releases the accumulator.  The
+// registers are 12 blocks of 8 columns; the block a column group goes to is warp-uniform.
+// (separate members and an if-chain: an array indexed through a switch is turned into a dynamically
+// indexed local-memory array by the compiler)
+struct DrainAcc {
+  float2 b0[4], b1[4], b2[4], b3[4], b4[4], b5[4], b6[4], b7[4], b8[4], b9[4], b10[4], b11[4];
+};
+#define BSK_TC_FOR_BLOCKS(X) X(0, b0) X(1, b1) X(2, b2) X(3, b3) X(4, b4) X(5, b5) X(6, b6) X(7, b7) X(8, b8) X(9, b9) X(10, b10) X(11, b11)
+__device__ __forceinline__ void add4(float2 (&a)[4], const float2 (&v)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a[c] = __fadd2_rn(a[c], v[c]);
+}
+__device__ __forceinline__ void add_block(DrainAcc& acc, int blk, const float2 (&v)[4]) {
+#define BSK_TC_ADD(K, M) if (blk == K) { add4(acc.M, v); return; }
+  BSK_TC_FOR_BLOCKS(BSK_TC_ADD)
+#undef BSK_TC_ADD
+}
+__device__ __forceinline__ void drain_unit(DrainAcc& acc, int blk0, int nblk, uint32_t d_tmem, uint32_t bar_full,
                                            uint32_t bar_empty, uint32_t parity, int lane, long long& prof_wait,
                                            long long& prof_work) {
   long long t0 = 0;
@@ -286,81 +414,158 @@ __device__ __forceinline__ void drain_unit(float2 (&acc)[cap(J) / 2], int ncol, 
   tc_wait(bar_full, parity);
   tc_fence_after();
   if constexpr (PROF) { const long long now = clock64(); prof_wait += now - t0; t0 = now; }
-#pragma unroll
-  for (int g0 = 0; g0 < cap(J) / 8; g0 += 3) {   // up to three 8-column groups in flight
-    if (g0 * 8 < ncol) {
-      float2 v[3][4];
-#pragma unroll
-      for (int g = 0; g < 3; ++g)
-        if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol) tmem_ld8v(d_tmem + (g0 + g) * 8, v[g]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int g = 0; g < 3; ++g)
-        if (g0 + g < cap(J) / 8 && (g0 + g) * 8 < ncol) {
-          pin8(v[g]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[(g0 + g) * 4 + c] = __fadd2_rn(acc[(g0 + g) * 4 + c], v[g][c]);
-        }
-    }
+#pragma unroll 1
+  for (int g0 = 0; g0 < nblk; ++g0) {   // one 8-column group at a time (the drain is not throughput critical)
+    float2 v0[4];
+    tmem_ld8v(d_tmem + g0 * 8, v0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    pin8(v0);
+    add_block(acc, blk0 + g0, v0);
   }
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(bar_empty);
   if constexpr (PROF) prof_work += clock64() - t0;
 }
-template <int J>
-__device__ __forceinline__ void flush_unit(float2 (&acc)[cap(J) / 2], int ncol, double* my_partial) {
-#pragma unroll
-  for (int c = 0; c < cap(J) / 2; ++c)
-    if (2 * c < ncol) {
-      atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c) * 128, (double)acc[c].x);
-      atomicAdd(my_partial + (int64_t)(capoff(J) + 2 * c + 1) * 128, (double)acc[c].y);
-      acc[c] = make_float2(0.f, 0.f);
-    }
-}
-template <int N>
-__device__ __forceinline__ void zero_acc(float2 (&acc)[N]) {
-#pragma unroll
-  for (int c = 0; c < N; ++c) acc[c] = make_float2(0.f, 0.f);
-}
 
 __device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint32_t tbase, int team, int q, int lane) {
-  float2 a0[cap(0) / 2], a1[cap(1) / 2], a2[cap(2) / 2], a3[cap(3) / 2];
-  zero_acc(a0); zero_acc(a1); zero_acc(a2); zero_acc(a3);
+  DrainAcc acc;
+#define BSK_TC_ZERO(K, M) _Pragma("unroll") for (int c = 0; c < 4; ++c) acc.M[c] = make_float2(0.f, 0.f);
+  BSK_TC_FOR_BLOCKS(BSK_TC_ZERO)
+#undef BSK_TC_ZERO
   const int my_nu = p.nu[team];
-  auto ncol = [&](int j) { return j < my_nu ? p.uncol[team * UPT + j] : 0; };
-  const uint32_t d_base = tbase + ((uint32_t)(q * 32) << 16) + TM_D + (uint32_t)team * CAPSUM;
+  int blk0[UPT], nblk[UPT];
+  int used = 0;
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) {
+    blk0[j] = p.ublk0[team * UPT + j];
+    nblk[j] = j < my_nu ? p.uncol[team * UPT + j] / 8 : 0;
+    used = max(used, blk0[j] + nblk[j]);
+  }
+  const uint32_t d_base = tbase + ((uint32_t)(q * 32) << 16) + TM_D + (uint32_t)team * TEAMCOLS;
   const uint32_t bar_full = bars + (D_FULL + team * UPT) * 8, bar_empty = bars + (D_EMPTY + team * UPT) * 8;
-  double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * p.partial_stride + q * 32 + lane;
+  double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * ((int64_t)TEAMCOLS * 128) + q * 32 + lane;
+  const uint64_t pol = policy_evict_last();
   int since_flush = 0;
   long long d_wait = 0, d_work = 0;
-  uint32_t n = 0;     // windows drained so far
+  uint32_t nwin[UPT];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) nwin[j] = 0;
   auto flush = [&]() {
-    flush_unit<0>(a0, ncol(0), my_partial); flush_unit<1>(a1, ncol(1), my_partial);
-    flush_unit<2>(a2, ncol(2), my_partial); flush_unit<3>(a3, ncol(3), my_partial);
+#define BSK_TC_FLUSH(K, M)                                                                         \
+  if (K < used) {                                                                                  \
+    _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                \
+      red_add_f64_hint(my_partial + (int64_t)(K * 8 + 2 * c) * 128, acc.M[c].x, pol);      \
+      red_add_f64_hint(my_partial + (int64_t)(K * 8 + 2 * c + 1) * 128, acc.M[c].y, pol);  \
+      acc.M[c] = make_float2(0.f, 0.f);                                                            \
+    }                                                                                              \
+  }
+    BSK_TC_FOR_BLOCKS(BSK_TC_FLUSH)
+#undef BSK_TC_FLUSH
   };
-#define BSK_TC_DRAIN(J, ACC)                                                                              \
-  if (J < my_nu)                                                                                          \
-    drain_unit<J>(ACC, ncol(J), d_base + capoff(J), bar_full + J * 8, bar_empty + J * 8, n & 1u, lane,    \
-                  d_wait, d_work);
-  for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t gtot = (uint32_t)(my_tiles * NCH);
 #pragma unroll 1
-    for (int c = 0; c < NCH / WIN; ++c) {
-      BSK_TC_DRAIN(0, a0) BSK_TC_DRAIN(1, a1) BSK_TC_DRAIN(2, a2) BSK_TC_DRAIN(3, a3)
-      ++n;
-      if ((since_flush += WIN) >= p.flush_chunks) {
-        flush();
-        since_flush = 0;
+  for (uint32_t g = 0; g < gtot; ++g) {
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) {
+      if (nblk[j] > 0 && win_closes(g, team * UPT + j, gtot)) {
+        drain_unit(acc, blk0[j], nblk[j], d_base + blk0[j] * 8, bar_full + j * 8, bar_empty + j * 8, nwin[j] & 1u, lane,
+                   d_wait, d_work);
+        ++nwin[j];
       }
     }
+    if (++since_flush >= p.flush_chunks) {
+      flush();
+      since_flush = 0;
+    }
   }
-#undef BSK_TC_DRAIN
   flush();
   if constexpr (PROF) {
     if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
-      p.prof[(NTEAMS + 1 + team) * 8 + 0] = d_wait;
-      p.prof[(NTEAMS + 1 + team) * 8 + 1] = d_work;
-      p.prof[(NTEAMS + 1 + team) * 8 + 2] = n;
+      p.prof[(2 * NTEAMS + team) * 8 + 0] = d_wait;
+      p.prof[(2 * NTEAMS + team) * 8 + 1] = d_work;
+      p.prof[(2 * NTEAMS + team) * 8 + 2] = nwin[0];
+    }
+  }
+}
+
+// MMA issuer of one team: 12 MMAs per unit and chunk into the unit's own accumulator
+__device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase, int team) {
+  const uint32_t leader = elect_one();
+  const int N = p.ncols;
+  const uint32_t lbo = (uint32_t)(N / 8) * 128u;     // next 4-cell group of the image
+  const int my_nu = p.nu[team];
+  uint32_t idesc[UPT], coff[UPT], dblk[UPT];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) {
+    dblk[j] = (uint32_t)p.ublk0[team * UPT + j];
+    idesc[j] = make_idesc_tf32(j < my_nu ? p.uncol[team * UPT + j] : 8);
+    coff[j] = (uint32_t)p.ucol0[team * UPT + j];     // first column, = 16-byte units into an image group
+  }
+  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t gtot = (uint32_t)(my_tiles * NCH);
+  uint32_t nwin[UPT];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) nwin[j] = 0;
+  uint32_t n_unit = 0, g = 0;
+  long long m_afull = 0, m_dempty = 0, m_issue = 0, m_bfull = 0, m_mark = 0, m_start = 0;
+  if constexpr (PROF) m_start = clock64();
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if constexpr (PROF) m_mark = clock64();
+    tc_wait(bars + (B_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
+    if constexpr (PROF) m_bfull += clock64() - m_mark;
+    const uint32_t img_hi = smem_u32(smem + OFF_BIMG + (buf * 2 + 0) * BIMG_BYTES);
+    const uint32_t img_lo = smem_u32(smem + OFF_BIMG + (buf * 2 + 1) * BIMG_BYTES);
+    // descriptor of (image, 4-cell group gq, first column col0): base + gq * N + col0 in 16-byte units
+    const uint32_t dh_lo = (uint32_t)make_desc(img_hi, lbo, 128u), dl_lo = (uint32_t)make_desc(img_lo, lbo, 128u);
+    const uint32_t d_hi32 = (uint32_t)(make_desc(img_hi, lbo, 128u) >> 32);
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++g) {
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) {
+        if (j >= my_nu) continue;
+        const int u = team * UPT + j;
+        const uint32_t n = n_unit++;
+        const uint32_t ab = n & 1u;
+        if constexpr (PROF) m_mark = clock64();
+        tc_wait(bars + (A_FULL + team * 2 + ab) * 8, (n >> 1) & 1u);
+        if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
+        const bool opens = win_opens(g, u);
+        if (opens)    // first chunk of a window: the unit's accumulator must have been drained
+          tc_wait(bars + (D_EMPTY + u) * 8, (nwin[j] & 1u) ^ 1u);
+        tc_fence_after();
+        if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
+        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + dblk[j] * 8u;
+        const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
+        const uint32_t id = idesc[j];
+        const uint32_t o0 = coff[j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
+        const bool closes = win_closes(g, u, gtot);
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < CH / 8; ++ks) {
+            const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
+            mma_tf32_ts(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id, (ks == 0 && opens) ? 0u : 1u);   // P_lo * C_hi
+            mma_tf32_ts(d, a + ks * 8, dl_lo + o, d_hi32, id, 1u);                                  // P_hi * C_lo
+            mma_tf32_ts(d, a + ks * 8, dh_lo + o, d_hi32, id, 1u);                                  // P_hi * C_hi
+          }
+          tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
+          if (closes) tc_commit(bars + (D_FULL + u) * 8);
+        }
+        if (closes) ++nwin[j];
+        __syncwarp();
+        if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
+      }
+    }
+    if (leader) tc_commit(bars + (B_EMPTY + buf) * 8);
+    __syncwarp();
+  }
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && p.prof) {
+      long long* o = p.prof + (NTEAMS + team) * 8;
+      o[0] = m_afull; o[1] = m_dempty; o[2] = m_issue; o[3] = m_bfull; o[4] = clock64() - m_start;
     }
   }
 }
@@ -371,33 +576,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
   const uint32_t bars = smem_u32(bar_ptr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = p.nrows, N = p.ncols;
-  constexpr int W_DRAIN = NTEAMS * 4, W_TMA = 2 * W_DRAIN, W_MMA = W_TMA + 1;
+  constexpr int W_DRAIN = NTEAMS * 4, W_TMA = 2 * W_DRAIN, W_MMA0 = W_TMA + 1, W_CONV = W_MMA0 + NTEAMS;
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < MAXRAWBUF; ++b) {
       mbar_init(&bar_ptr[RAW_FULL + b], 1);
-      mbar_init(&bar_ptr[RAW_EMPTY + b], NTEAMS * 4 + 2);
-      mbar_init(&bar_ptr[B_FULL + b], 2);
-      mbar_init(&bar_ptr[B_EMPTY + b], 1);
+      mbar_init(&bar_ptr[RAW_EMPTY + b], NTEAMS * 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_ptr[B_FULL + b], NTEAMS * 4);
+      mbar_init(&bar_ptr[B_EMPTY + b], NTEAMS);
     }
     for (int b = 0; b < 2 * NTEAMS; ++b) {
       mbar_init(&bar_ptr[A_FULL + b], 4);
       mbar_init(&bar_ptr[A_EMPTY + b], 1);
     }
-    for (int b = 0; b < NTEAMS * UPT; ++b) {
+    for (int b = 0; b < NUNITS; ++b) {
       mbar_init(&bar_ptr[D_FULL + b], 1);
       mbar_init(&bar_ptr[D_EMPTY + b], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero row of both raw buffers and the whole operand-image area (rows R..N-1 stay zero)
-  for (int i = tid; i < RAW_STRIDE / 4; i += NTHREADS) {
-    reinterpret_cast<uint32_t*>(smem + OFF_RAW + R * RAW_STRIDE)[i] = 0u;
-    reinterpret_cast<uint32_t*>(smem + OFF_RAW + RAW_BYTES + R * RAW_STRIDE)[i] = 0u;
-  }
-  for (int i = tid; i < 4 * BIMG_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem + OFF_BIMG)[i] = 0u;
-  if (warp == W_MMA) {
+  // the operand images and every raw buffer (rows that are never loaded must read as zero)
+  for (int i = tid; i < (4 * BIMG_BYTES + p.nbuf * p.rawb) / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(smem + OFF_BIMG)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == W_MMA0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -408,136 +611,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   const uint32_t tbase = *tmem_slot;
 
   if (warp < W_DRAIN) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_TEAM));
-    team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);
+    team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);     // keeps its 96 registers
   } else if (warp < W_TMA) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
     drain_loop(p, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     if (warp == W_TMA) {
-      // ---- TMA producer
+      // ---- TMA producer: raw [row][cell] tiles, nbuf - 1 tiles ahead of the generators
+      const uint64_t pol = policy_evict_first();
+      // this lane's raw rows (slots lane, lane + 32, ...): pointers of the rows that are really loaded
+      const float* src[(MAXRAW + 31) / 32];
+      int nload = 0;
+#pragma unroll
+      for (int k = 0; k < (MAXRAW + 31) / 32; ++k) {
+        const int sl = lane + 32 * k;
+        const int r = sl < p.nraw ? p.rawrow[sl] : -1;
+        src[k] = r >= 0 ? p.rowptr[r] : nullptr;
+        nload += r >= 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nload += __shfl_xor_sync(0xffffffffu, nload, o);
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        tc_wait(bars + (RAW_EMPTY + buf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        if (lane == 0) mbar_expect_tx(&bar_ptr[RAW_FULL + buf], (uint32_t)(R * TL * 4));
+        const int buf = it % p.nbuf;
+        tc_wait(bars + (RAW_EMPTY + buf) * 8, ((uint32_t)(it / p.nbuf) & 1u) ^ 1u);
+        if (lane == 0) mbar_expect_tx(&bar_ptr[RAW_FULL + buf], (uint32_t)(nload * TL * 4));
         __syncwarp();
-        unsigned char* dst = smem + OFF_RAW + buf * RAW_BYTES;
-        for (int r = lane; r < R; r += 32)
-          bulk_g2s(dst + r * RAW_STRIDE, p.rowptr[r] + tile * TL, TL * 4, &bar_ptr[RAW_FULL + buf]);
+        unsigned char* dst = const_cast<unsigned char*>(smem) + OFF_RAW + buf * p.rawb;
+#pragma unroll
+        for (int k = 0; k < (MAXRAW + 31) / 32; ++k)
+          if (src[k]) bulk_g2s_hint(dst + (lane + 32 * k) * RAW_STRIDE, src[k] + tile * TL, TL * 4, &bar_ptr[RAW_FULL + buf], pol);
       }
-    } else if (warp == W_MMA) {
-      // ---- MMA issuer
-      const uint32_t leader = elect_one();
-      const uint32_t lbo = (uint32_t)(N / 8) * 128u;     // next 4-cell group of the image
-      uint32_t n_unit[NTEAMS];
-      uint32_t idesc[NTEAMS * UPT], coff[NTEAMS * UPT];
-#pragma unroll
-      for (int t = 0; t < NTEAMS; ++t) n_unit[t] = 0u;
-#pragma unroll
-      for (int i = 0; i < NTEAMS * UPT; ++i) {
-        idesc[i] = make_idesc_tf32(p.uncol[i]);
-        coff[i] = (uint32_t)p.ucol0[i];                  // first column, = 16-byte units into an image group
-      }
-      long long m_afull = 0, m_dempty = 0, m_issue = 0, m_bfull = 0, m_mark = 0, m_start = 0;
-      if constexpr (PROF) m_start = clock64();
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if constexpr (PROF) m_mark = clock64();
-        tc_wait(bars + (B_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
-        if constexpr (PROF) m_bfull += clock64() - m_mark;
-        const uint32_t img_hi = smem_u32(smem + OFF_BIMG + (buf * 2 + 0) * BIMG_BYTES);
-        const uint32_t img_lo = smem_u32(smem + OFF_BIMG + (buf * 2 + 1) * BIMG_BYTES);
-        // descriptor of (image, 4-cell group g, first column col0): base + g * N + col0 in 16-byte units
-        const uint32_t dh_lo = (uint32_t)make_desc(img_hi, lbo, 128u), dl_lo = (uint32_t)make_desc(img_lo, lbo, 128u);
-        const uint32_t d_hi32 = (uint32_t)(make_desc(img_hi, lbo, 128u) >> 32);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const uint32_t n_win = (uint32_t)it * (NCH / WIN) + (uint32_t)(c / WIN);
-#pragma unroll
-          for (int j = 0; j < UPT; ++j) {
-#pragma unroll
-            for (int team = 0; team < NTEAMS; ++team) {
-              if (j >= p.nu[team]) continue;
-              const uint32_t n = n_unit[team]++;
-              const uint32_t ab = n & 1u;
-              if constexpr (PROF) m_mark = clock64();
-              tc_wait(bars + (A_FULL + team * 2 + ab) * 8, (n >> 1) & 1u);
-              if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
-              if (c % WIN == 0)    // first chunk of a window: the unit's accumulator must have been drained
-                tc_wait(bars + (D_EMPTY + team * UPT + j) * 8, (n_win & 1u) ^ 1u);
-              tc_fence_after();
-              if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
-              const uint32_t d = tbase + TM_D + (uint32_t)team * CAPSUM + capoff(j);
-              const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
-              const uint32_t id = idesc[team * UPT + j];
-              const uint32_t o0 = coff[team * UPT + j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
-              if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < CH / 8; ++ks) {
-                  const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
-                  if (ks == 0 && c % WIN == 0) mma_tf32_ts2<0>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);   // P_lo * C_hi
-                  else mma_tf32_ts2<1>(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id);
-                  mma_tf32_ts2<1>(d, a + ks * 8, dl_lo + o, d_hi32, id);                       // P_hi * C_lo
-                  mma_tf32_ts2<1>(d, a + ks * 8, dh_lo + o, d_hi32, id);                       // P_hi * C_hi
-                }
-                tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
-                if (c % WIN == WIN - 1) tc_commit(bars + (D_FULL + team * UPT + j) * 8);
-              }
-              __syncwarp();
-              if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
-            }
-          }
-        }
-        if (leader) tc_commit(bars + (B_EMPTY + buf) * 8);
-        __syncwarp();
-      }
-      if constexpr (PROF) {
-        if (blockIdx.x == 0 && lane == 0 && p.prof) {
-          long long* o = p.prof + NTEAMS * 8;
-          o[0] = m_afull; o[1] = m_dempty; o[2] = m_issue; o[3] = m_bfull; o[4] = clock64() - m_start;
-        }
-      }
+    } else if (warp == W_CONV) {
+      // spare warp
     } else {
-      // ---- operand-image converters (64 threads): raw fp32 -> tf32 hi (round to nearest) + lo
-      const int ct = tid - (W_MMA + 1) * 32;
-      const uint32_t ngrp = (uint32_t)(N / 8) * 128u;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it >> 1) & 1u);
-        tc_wait(bars + (B_EMPTY + buf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        const uint32_t raw = smem_u32(smem + OFF_RAW + buf * RAW_BYTES);
-        const uint32_t img_hi = smem_u32(smem + OFF_BIMG + (buf * 2 + 0) * BIMG_BYTES);
-        const uint32_t img_lo = smem_u32(smem + OFF_BIMG + (buf * 2 + 1) * BIMG_BYTES);
-        for (int i = ct; i < R * (TL / 4); i += 64) {
-          const int g = i / R, l = i - g * R;          // consecutive threads: consecutive rows
-          const float4 v = lds128(raw + (uint32_t)l * RAW_STRIDE + (uint32_t)g * 16u);
-          const float x[4] = {v.x, v.y, v.z, v.w};
-          uint32_t h[4], lo[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            h[k] = (__float_as_uint(x[k]) + 0x1000u) & 0xFFFFE000u;
-            lo[k] = __float_as_uint(x[k] - __uint_as_float(h[k]));
-          }
-          const uint32_t o = (uint32_t)g * ngrp + (uint32_t)(l >> 3) * 128u + (uint32_t)(l & 7) * 16u;
-          sts128(img_hi + o, h[0], h[1], h[2], h[3]);
-          sts128(img_lo + o, lo[0], lo[1], lo[2], lo[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bars + (B_FULL + buf) * 8);
-          mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
-        }
-      }
+      mma_loop(p, smem, bars, tbase, warp - W_MMA0);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+  if (warp == W_MMA0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
 }
 
 }  // namespace tc

@@ -272,6 +272,54 @@ def measure_unnormalized(meshes, box, edges, triples, pos_units=1.0,
     return out
 
 
+def measure_unnormalized_dense(meshes, box, edges, triples, pos_units=1.0, workers=None,
+                               progress=False):
+    """Same numbers as :func:`measure_unnormalized` (main.py:1871-1882) for long triangle lists
+    on large grids: every shell is built once (as the reference's fast path does,
+    main.py:1846-1861), the product I_a*I_b is formed once per (a,b) pair and the full-grid sum
+    ``np.sum((I_a*I_b)*I_c)`` is evaluated as a float64 dot product, x-slabs on a thread pool.
+    Used to generate the committed 512^3 fixture (scripts/make_golden_metric512.py)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import time
+    fields = [np.asarray(m, dtype=np.float64) for m in meshes]
+    n = fields[0].shape[0]
+    delta_k = [forward(f, workers) for f in fields]
+    del fields
+    L = _box3(box)
+    kk = k_norm(n, L)
+    edges = np.asarray(edges, dtype=np.float64)
+    triples = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    route = _route(len(delta_k))
+    shells = {}
+    for slot in range(3):
+        for ibin in np.unique(triples[:, slot]):
+            key = (route[slot], int(ibin))
+            if key not in shells:
+                shells[key] = data_shell(delta_k[key[0]], kk, edges[ibin, 0], edges[ibin, 1], workers)
+    del kk, delta_k
+    nw = max(1, int(workers or 1))
+    slabs = [(int(s[0]), int(s[-1]) + 1) for s in np.array_split(np.arange(n), min(nw, n)) if len(s)]
+    pool = ThreadPoolExecutor(nw)
+    norm = L.prod() ** 2 / float(n) ** 3
+    out = np.empty(len(triples))
+    order = np.lexsort((triples[:, 2], triples[:, 1], triples[:, 0]))
+    prod = np.empty((n, n, n))
+    last = None
+    t0 = time.time()
+    for cnt, t in enumerate(order):
+        a, b, c = (int(v) for v in triples[t])
+        fa, fb, fc = shells[(route[0], a)], shells[(route[1], b)], shells[(route[2], c)]
+        if last != (a, b):
+            list(pool.map(lambda s: np.multiply(fa[s[0]:s[1]], fb[s[0]:s[1]], out=prod[s[0]:s[1]]), slabs))
+            last = (a, b)
+        parts = pool.map(lambda s: float(np.dot(prod[s[0]:s[1]].reshape(-1), fc[s[0]:s[1]].reshape(-1))), slabs)
+        out[t] = sum(parts) * norm * pos_units ** 6.0
+        if progress and cnt % 500 == 0:
+            print(f"  triangle {cnt}/{len(order)}  {time.time() - t0:.0f}s", flush=True)
+    pool.shutdown()
+    return out
+
+
 def measure_gridinfo(nmesh, box, edges, triples, pos_units=1.0, workers=None):
     """(N_tri, k_mean[T,3]) per triple (main.py:2006-2064).
 

@@ -72,8 +72,9 @@ def test_no_cpu_fallback():
 
 def test_tensor_core_schedule_is_injective_and_pruned():
     """Host logic of the tcgen05 contraction (no device): every triangle of a dense list reads
-    its own accumulator slot (pair row x column), the S=40 all-triangle list needs 7 units whose
-    column counts sum to 184 (vs 7 x 40 dense), and lists that do not fit are reported ineligible."""
+    its own accumulator slot (pair row x column); the class cover needs fewer 128-row units than
+    one pair row per row pair would (S=40: 5 units instead of 7); lists that do not fit one launch
+    (S=80, cross lists) are cut into passes; short lists are reported ineligible."""
     import ctypes as C
     import numpy as np
     from bskit_b200 import _native
@@ -84,24 +85,32 @@ def test_tensor_core_schedule_is_injective_and_pruned():
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         out = (C.c_int64 * 6)()
         assert lib.bsk_tc_schedule_info(len(rows), rows.ctypes.data_as(C.POINTER(C.c_int32)), nrows, out) == 0
-        return list(out)
+        return dict(units=out[0], distinct=out[1], cols=out[2], passes=out[3], in_range=out[4], cost=out[5])
 
     kf = 2 * np.pi / 1000.0
-    for nb, units, cols in ((40, 7, 184), (24, 5, None), (12, 3, None)):
-        idx = generate_triangle_bin_list(kmin=0.5 * kf, kmax=(nb + 1.0) * kf, dk=kf, return_indices=True)
-        assert idx.max() == nb - 1
-        got = info(idx, (nb + 3) // 4 * 4)
-        assert got[0] == units, got
-        assert got[1] == len(idx) and got[4] == 1          # injective, in range
-        if cols:
-            assert got[2] == cols
-        assert got[3] == nb * (nb + 1) // 2 and got[3] <= 128 * units     # one pair row per row pair
+
+    def all_list(nb, nf=1):
+        idx = generate_triangle_bin_list(kmin=0.5 * kf, kmax=(nb + 1.0) * kf, dk=kf, num_fields=nf,
+                                         return_indices=True)
+        seg = (nb + 3) // 4 * 4
+        return np.asarray(idx) + np.array([0, 0, seg if nf == 2 else 0]), seg * nf
+
+    for nb, max_units, max_passes in ((40, 6, 2), (24, 3, 1), (12, 2, 1), (80, 32, 9)):
+        idx, nrows = all_list(nb)
+        got = info(idx, nrows)
+        assert 0 < got["units"] <= max_units and got["passes"] <= max_passes, got
+        assert got["distinct"] == len(idx) and got["in_range"] == 1, got      # injective, in range
+        assert got["cols"] <= 96 * 2 * got["passes"], got                     # TMEM accumulator budget
+    # two-field <AAB> list: 80 rows, the third row lives in the second segment
+    idx, nrows = all_list(40, 2)
+    got = info(idx, nrows)
+    assert got["units"] > 0 and got["distinct"] == len(idx) and got["in_range"] == 1, got
     # random dense list over 40 rows in arbitrary row order: still injective
     rng = np.random.default_rng(0)
     tri = np.array([[a, b, c] for a in range(40) for b in range(a, 40) for c in range(b, 40) if (a + b + c) % 3 == 0])
     tri = np.array([rng.permutation(t) for t in tri])
     got = info(tri, 40)
-    assert got[0] > 0 and got[1] == len(tri) and got[4] == 1
-    # not eligible: too many rows, too few triangles
-    assert info(np.array([[a, a, a] for a in range(80)] * 4), 80)[0] == 0
-    assert info(np.array([[0, 1, 2]]), 4)[0] == 0
+    assert got["units"] > 0 and got["distinct"] == len(tri) and got["in_range"] == 1
+    # not eligible: too few triangles
+    assert info(np.array([[a, a, a] for a in range(80)]), 80)["units"] == 0
+    assert info(np.array([[0, 1, 2]]), 4)["units"] == 0
