@@ -19,7 +19,7 @@ MAX_CHUNK = 64
 #: every symbol include/bskit_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
-    "bsk_set_compensation", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
+    "bsk_set_compensation", "bsk_plan_set_stream", "bsk_fold_even", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
     "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_cplan_set_path",
     "bsk_cplan_path", "bsk_tc_schedule_info", "bsk_contract",
     "bsk_reduce_list", "bsk_paint_cic", "bsk_launch_count",
@@ -64,6 +64,8 @@ def lib():
     L.bsk_plan_destroy.argtypes = [vp]
     L.bsk_plan_info.argtypes = [vp, C.POINTER(Info)]
     L.bsk_set_compensation.argtypes = [vp, dp, dp, dp]
+    L.bsk_plan_set_stream.argtypes = [vp, vp]
+    L.bsk_fold_even.argtypes = [vp, ip, ip, ip, ip, ip, vp, C.c_int64, vp]
     L.bsk_forward_local.argtypes = [vp, vp, ip, vp, vp, vp]
     L.bsk_forward_finish.argtypes = [vp, vp, vp]
     L.bsk_modes_per_bin.argtypes = [vp, ip, dp, dp, C.POINTER(C.c_int64)]

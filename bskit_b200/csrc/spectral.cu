@@ -209,6 +209,36 @@ __global__ void scatter_planes_kernel(const typename Cx<T>::type* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------
+// Even-field fold.  Unit-amplitude and |k|-weighted shells depend on |k| only, so they are even in
+// every axis: sum_x f g h over the grid = sum over [0, M/2] per mirrored axis of w f g h with
+// w = prod_axis (1 on the planes 0 and M/2, 2 elsewhere).  Scaling each field by w^(1/3) puts the
+// weight into the triple product, so the normalisation (main.py:2024-2061) contracts nx*h*h cells
+// instead of mxl*M*M.  out rows are zero-padded to `ncell_out` (a multiple of 4).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void fold_even_kernel(const T* __restrict__ fields, T* __restrict__ out, int nrows, int M, int mxl,
+                                 int nx, int fold_x, int64_t ncell_out) {
+  const int h = M / 2 + 1;
+  const int64_t nred = (int64_t)nx * h * h;
+  const double c1 = 1.0, c2 = 1.2599210498948731648;   // 2^(1/3)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)nrows * ncell_out;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ncell_out);
+    const int64_t c = i - (int64_t)r * ncell_out;
+    T v = (T)0;
+    if (c < nred) {
+      const int z = (int)(c % h);
+      const int64_t t = c / h;
+      const int y = (int)(t % h), x = (int)(t / h);
+      double w = ((y == 0 || y == h - 1) ? c1 : c2) * ((z == 0 || z == h - 1) ? c1 : c2);
+      if (fold_x) w *= (x == 0 || x == h - 1) ? c1 : c2;
+      v = (T)((double)fields[((int64_t)r * mxl + x) * M * M + (int64_t)y * M + z] * w);
+    }
+    out[i] = v;
+  }
+}
+
 static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
   int64_t g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -505,6 +535,42 @@ int bsk_set_compensation(bsk_plan* p, const double* cx, const double* cy, const 
   BSK_CUDA(cudaMemcpyAsync(p->d_cz, sz, sizeof(double) * p->info.kz, cudaMemcpyHostToDevice, p->stream));
   BSK_CUDA(cudaStreamSynchronize(p->stream));
   p->has_comp = cx || cy || cz;
+  return BSK_OK;
+}
+
+int bsk_plan_set_stream(bsk_plan* p, void* cuda_stream) {
+  BSK_REQUIRE(p, "bsk_plan_set_stream: null plan");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (st == p->stream) return BSK_OK;
+  p->stream = st;
+  if (p->fwd2d) BSK_FFT(cufftSetStream(p->fwd2d, st));
+  if (p->fwdx) BSK_FFT(cufftSetStream(p->fwdx, st));
+  for (auto& kv : p->invx) BSK_FFT(cufftSetStream(kv.second, st));
+  for (auto& kv : p->inv2d) BSK_FFT(cufftSetStream(kv.second, st));
+  for (auto& kv : p->invy) BSK_FFT(cufftSetStream(kv.second, st));
+  return BSK_OK;
+}
+
+int bsk_fold_even(const void* fields, int precision, int nrows, int neval, int mxl, int fold_x, void* out,
+                  int64_t ncell_out, void* cuda_stream) {
+  BSK_REQUIRE(fields && out && nrows > 0 && neval >= 4 && neval % 2 == 0 && mxl >= 1,
+              "bsk_fold_even: bad argument");
+  BSK_REQUIRE(precision == BSK_F32 || precision == BSK_F64, "bsk_fold_even: bad precision");
+  const int h = neval / 2 + 1;
+  const int nx = fold_x ? h : mxl;
+  BSK_REQUIRE(!fold_x || mxl == neval, "bsk_fold_even: the x axis can only be folded when the whole grid is local");
+  BSK_REQUIRE(ncell_out >= (int64_t)nx * h * h && ncell_out % 4 == 0,
+              "bsk_fold_even: ncell_out must be a multiple of 4 and hold nx*(M/2+1)^2 cells");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t total = (int64_t)nrows * ncell_out;
+  if (precision == BSK_F64)
+    fold_even_kernel<double><<<grid_for(total, 256), 256, 0, st>>>((const double*)fields, (double*)out, nrows, neval,
+                                                                    mxl, nx, fold_x, ncell_out);
+  else
+    fold_even_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)fields, (float*)out, nrows, neval, mxl,
+                                                                   nx, fold_x, ncell_out);
+  count_launch();
+  BSK_CUDA(cudaGetLastError());
   return BSK_OK;
 }
 

@@ -159,7 +159,7 @@ class NativeBackend:
     name = "cuda-sm100a"
 
     def __init__(self, grid: GridChoice, boxsize, precision, world, rank, device, max_shells,
-                 fft_precision=None, accum_precision=None, no_prune=False):
+                 fft_precision=None, accum_precision=None, no_prune=False, contraction=None):
         if device.type != "cuda":
             raise nat.NativeError("bskit_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = nat.lib()
@@ -181,12 +181,27 @@ class NativeBackend:
         self.handle = handle
         self.info = nat.Info()
         nat.check(self.lib.bsk_plan_info(handle, C.byref(self.info)), "bsk_plan_info")
-        self._cplans = {}
-        #: 1 = tcgen05 tensor cores for eligible dense lists (default; 3xTF32, ~1e-6 relative),
-        #: 0 = FP32-pipe tile kernel everywhere (exact round-to-nearest products, ~5e-8;
-        #: BSKIT_B200_CONTRACTION=fp32).  include/bskit_b200.h, bsk_cplan_set_path
-        self.contraction_path = 0 if os.environ.get("BSKIT_B200_CONTRACTION", "") == "fp32" else 1
+        self._cplans = {}           # insertion-ordered: least recently used first
+        #: 1 = tcgen05 tensor cores for eligible dense lists (3xTF32), 0 = FP32-pipe tile kernel
+        #: everywhere (exact round-to-nearest products).  Chosen by the `contraction` argument
+        #: ('tensor' | 'fp32'), else BSKIT_B200_CONTRACTION, else tensor.
+        #: include/bskit_b200.h, bsk_cplan_set_path
+        if contraction is None:
+            contraction = os.environ.get("BSKIT_B200_CONTRACTION", "") or "tensor"
+        if contraction not in ("tensor", "fp32"):
+            raise ValueError("contraction must be 'tensor' or 'fp32'")
+        self.contraction_path = 0 if contraction == "fp32" else 1
         self.last_path = 0
+
+    MAX_CPLANS = 8
+
+    def _use_current_stream(self):
+        """Every stage runs on the stream that is current when it is called (a plan built under
+        one stream may be used under another: sessions are cached across objects)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if st != self.stream:
+            nat.check(self.lib.bsk_plan_set_stream(self.handle, C.c_void_p(st)), "bsk_plan_set_stream")
+            self.stream = st
 
     def close(self):
         if getattr(self, "handle", None):
@@ -205,6 +220,7 @@ class NativeBackend:
     def set_compensation(self, tables):
         if tables is None and not getattr(self, "_has_comp", False):
             return                                   # already all ones: skip the upload + sync
+        self._use_current_stream()
         self._has_comp = tables is not None
         cx, cy, cz = tables if tables is not None else (None, None, None)
         nat.check(self.lib.bsk_set_compensation(self.handle, nat.dptr(cx), nat.dptr(cy), nat.dptr(cz)),
@@ -212,6 +228,7 @@ class NativeBackend:
 
     def forward_local(self, slab):
         """slab: CUDA tensor [nxl][N][N] f32/f64 -> planes_local [nxl][Ky][Kz] complex128."""
+        self._use_current_stream()
         f, n = self.info, self.grid.nmesh
         work = torch.empty(f.fwd_work_complex, dtype=torch.complex128, device=self.device)
         conv = None
@@ -225,6 +242,7 @@ class NativeBackend:
         return planes
 
     def forward_finish(self, planes_all):
+        self._use_current_stream()
         f = self.info
         cube = torch.empty((f.kx, f.ky, f.kz), dtype=torch.complex128, device=self.device)
         nat.check(self.lib.bsk_forward_finish(self.handle, planes_all.data_ptr(), cube.data_ptr()),
@@ -232,6 +250,7 @@ class NativeBackend:
         return cube
 
     def modes_per_bin(self, lo, hi):
+        self._use_current_stream()
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         out = np.zeros(len(lo), dtype=np.int64)
@@ -241,10 +260,12 @@ class NativeBackend:
         return out
 
     def prepare_shells(self, nsh):
+        self._use_current_stream()
         with torch.cuda.device(self.device):
             nat.check(self.lib.bsk_shells_prepare(self.handle, int(nsh)), "bsk_shells_prepare")
 
     def shells(self, cube, kind, kpow, lo, hi, xcols, planes2d, fields_out):
+        self._use_current_stream()
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         nat.check(self.lib.bsk_shells(self.handle, cube.data_ptr() if cube is not None else None,
@@ -261,17 +282,20 @@ class NativeBackend:
         job_off = np.ascontiguousarray(job_off, dtype=np.int32).reshape(-1, 3)
         njobs = len(job_off)
         key = (rows.tobytes(), nrows)
-        ent = self._cplans.get(key)
+        ent = self._cplans.pop(key, None)           # re-inserted below: most recently used last
         if ent is None or ent[1] < njobs:
             if ent is not None:
                 self.lib.bsk_cplan_destroy(ent[0])
+            while len(self._cplans) >= self.MAX_CPLANS:      # schedules hold device tables and partials
+                old = self._cplans.pop(next(iter(self._cplans)))
+                self.lib.bsk_cplan_destroy(old[0])
             cp = C.c_void_p()
             with torch.cuda.device(self.device):
                 nat.check(self.lib.bsk_cplan_create(C.byref(cp), len(rows),
                                                     rows.ctypes.data_as(C.POINTER(C.c_int32)),
                                                     nrows, max(njobs, 4)), "bsk_cplan_create")
             ent = (cp, max(njobs, 4))
-            self._cplans[key] = ent
+        self._cplans[key] = ent
         cp = ent[0]
         self._last_cplan = cp
         nat.check(self.lib.bsk_cplan_set_path(cp, int(self.contraction_path)), "bsk_cplan_set_path")
@@ -287,6 +311,22 @@ class NativeBackend:
         nat.check(self.lib.bsk_cplan_path(cp, out), "bsk_cplan_path")
         self.last_path = int(out[2])
         return sums
+
+    def fold_even(self, table, neval, mxl, fold_x):
+        """Octant (or y-z quadrant) of even fields with the cube-root multiplicity weights
+        (bsk_fold_even).  table: [nrows][mxl*M*M] contiguous; returns [nrows][ncell_out]."""
+        h = neval // 2 + 1
+        nx = h if fold_x else mxl
+        ncell_out = (nx * h * h + 3) // 4 * 4
+        out = torch.empty((table.shape[0], ncell_out), dtype=table.dtype, device=table.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.bsk_fold_even(C.c_void_p(table.data_ptr()),
+                                             nat.F32 if table.dtype == torch.float32 else nat.F64,
+                                             int(table.shape[0]), int(neval), int(mxl), int(bool(fold_x)),
+                                             C.c_void_p(out.data_ptr()), ncell_out,
+                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                      "bsk_fold_even")
+        return out
 
     def reduce_list(self, fields, rows, ncells):
         """Streaming per-triangle reduction for sparse lists; rows: (T,3) indices into fields.
@@ -321,7 +361,7 @@ class Engine:
 
     def __init__(self, grid: GridChoice, boxsize, precision=nat.F32, device=None, group=None,
                  backend_cls=NativeBackend, scratch_bytes=None, fft_precision=None,
-                 accum_precision=None, no_prune=False, max_rows=None):
+                 accum_precision=None, no_prune=False, max_rows=None, contraction=None):
         self.grid = grid
         self.max_rows = max_rows
         self.last_batches = 0
@@ -350,7 +390,8 @@ class Engine:
         self.chunk = int(max(1, min(nat.MAX_CHUNK, scratch_bytes // max(per_shell, 1), by_elems)))
         self.backend = backend_cls(grid, self.boxsize, precision, self.world, self.rank,
                                    self.device, self.chunk, fft_precision=fft_precision,
-                                   accum_precision=accum_precision, no_prune=no_prune)
+                                   accum_precision=accum_precision, no_prune=no_prune,
+                                   **({} if contraction is None else {"contraction": contraction}))
         self.info = self.backend.info
         self.ncells = int(self.info.field_real_per_shell)
         self.rdtype = torch.float32 if precision == nat.F32 else torch.float64
@@ -395,6 +436,9 @@ class Engine:
             return self.local_slab(mesh), None
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
+        # device inputs that need a cast / contiguous copy are read by a kernel on the copy stream:
+        # it must see what the caller's stream has written
+        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._copy_stream):
             slab = self.local_slab(mesh)
             ev = torch.cuda.Event()
@@ -574,10 +618,22 @@ def _alloc_table(shape, engine):
         print(f"[bsk] table {shape} {engine.rdtype} = {shape[0]*shape[1]*engine.itemsize/2**30:.1f} GiB; free {free/2**30:.1f} "
               f"reserved {torch.cuda.memory_reserved(engine.device)/2**30:.1f} allocated "
               f"{torch.cuda.memory_allocated(engine.device)/2**30:.1f} rowcap {engine.row_capacity()}", flush=True)
+    table, oom = None, 0
     try:
-        return torch.empty(shape, dtype=engine.rdtype, device=engine.device)
+        table = torch.empty(shape, dtype=engine.rdtype, device=engine.device)
     except torch.OutOfMemoryError:
-        pass
+        oom = 1
+    if engine.world > 1:
+        # every rank must take the same path (the retry invalidates the cached row capacity, whose
+        # re-measurement is collective): agree on "somebody ran out of memory"
+        flag = torch.tensor([oom], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=engine.group)
+        any_oom = int(flag.item())
+    else:
+        any_oom = oom
+    if not any_oom:
+        return table
+    del table
     engine._row_cap = None
     torch.cuda.empty_cache()
     return torch.empty(shape, dtype=engine.rdtype, device=engine.device)
@@ -637,26 +693,15 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
         job_off = np.asarray(job_seg_off, dtype=np.int64) * seg
         m = engine.grid.neval
         mxl = table.shape[1] // (m * m)
-        if symmetric and m % 2 == 0 and table.shape[1] == mxl * m * m and (engine.world > 1 or mxl == m):
+        if (symmetric and m % 2 == 0 and table.shape[1] == mxl * m * m and (engine.world > 1 or mxl == m)
+                and hasattr(engine.backend, "fold_even")):
             # Unit-amplitude and |k|-weighted shells depend on |k| only, so they are even in every
             # axis: f(x,y,z) = f(-x,y,z) = ...  The sum over the grid is the sum over [0, M/2] per
             # mirrored axis with multiplicity w = prod w_axis (1 on the planes 0 and M/2, else 2).
             # Scaling every field by w^(1/3) puts the weight into the triple product, so one
             # contraction over the reduced cells replaces the full-grid one: all three axes on one
             # GPU (8x fewer cells), y and z on this rank's x-slab otherwise (4x fewer).
-            h = m // 2 + 1
-            w1 = torch.full((h,), 2.0, dtype=torch.float64, device=table.device)
-            w1[0] = 1.0
-            w1[h - 1] = 1.0
-            if engine.world == 1:
-                nx, wx = h, w1
-            else:
-                nx, wx = mxl, torch.ones(mxl, dtype=torch.float64, device=table.device)
-            w3 = (wx[:, None, None] * w1[None, :, None] * w1[None, None, :]) ** (1.0 / 3.0)
-            nred = nx * h * h
-            ncell_o = (nred + 3) // 4 * 4
-            octant = torch.zeros((table.shape[0], ncell_o), dtype=table.dtype, device=table.device)
-            octant[:, :nred] = (table.view(-1, mxl, m, m)[:, :nx, :h, :h] * w3.to(table.dtype)).reshape(table.shape[0], -1)
+            octant = engine.backend.fold_even(table, m, mxl, fold_x=engine.world == 1)
             ofields = []
             for sidx in range(nseg):
                 ofields += [octant[sidx * nb + r] for r in range(nb)] + [octant[sidx * nb]] * (seg - nb)
@@ -703,6 +748,11 @@ def measure_grid_sums(engine: Engine, edges, triples, marks=None):
     jobs = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
     sums = _batched_contract(engine, 2, synth, jobs, uniq, marks, symmetric=True) / float(engine.grid.neval) ** 3
     ntri = np.rint(sums[0])                      # an exact triangle count (integer valued)
+    resid = float(np.max(np.abs(sums[0] - ntri))) if len(ntri) else 0.0
+    engine.last_ntri_residual = resid
+    if not resid < 0.05:
+        raise nat.NativeError(f"N_tri is not integer valued (max |N_tri - round| = {resid:.3g}): the "
+                              "float64 normalisation contraction has lost precision")
     with np.errstate(divide="ignore", invalid="ignore"):
         kmean = np.where(ntri[None, :] > 0, sums[1:4] / ntri[None, :], np.nan).T
     return ntri[inverse], np.ascontiguousarray(kmean[inverse])

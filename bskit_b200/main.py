@@ -46,7 +46,7 @@ __all__ = [
     "generate_triangle_bin_list",
     "number_field", "k_field", "pk_FFT", "compute_Nbin", "compute_k_means_on_grid",
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
-    "combine_gridinfo_and_unnormalized", "clear_cache",
+    "combine_gridinfo_and_unnormalized", "clear_cache", "set_gridinfo_cache",
     "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "measure_subboxes",
     "downsample_mesh", "paint_cic",
 ]
@@ -66,9 +66,14 @@ _BACKEND_FOR_TESTS = None
 class _Session:
     """Engines for one (Nmesh, BoxSize) pair on this process's GPU."""
 
+    MAX_ENGINES = 4     # each engine owns cuFFT plans and synthesis scratch (GiBs on a full 512^3 grid)
+
     def __init__(self, nmesh, boxsize, grid="auto", device=None, group=None, fft_dtype=None,
-                 accum_dtype=None):
+                 accum_dtype=None, contraction=None):
         from . import engine as eng
+        if contraction not in (None, "tensor", "fp32"):
+            raise ValueError("contraction must be 'tensor' or 'fp32'")
+        self.contraction = contraction
         self.fft_precision = None if fft_dtype is None else (F32 if np.dtype(fft_dtype) == np.float32 else F64)
         self.accum_precision = None if accum_dtype is None else (F32 if np.dtype(accum_dtype) == np.float32 else F64)
         self.eng = eng
@@ -84,13 +89,20 @@ class _Session:
         choice = self.eng.choose_grid(self.nmesh, self.boxsize, kmax,
                                       self.grid_policy if policy is None else policy, self.world)
         key = (choice, precision)
-        if key not in self._engines:
+        e = self._engines.pop(key, None)            # re-inserted below: most recently used last
+        if e is None:
+            # slow-path callers measure chunk after chunk with a different crop radius each: keep
+            # the few most recently used engines, close the rest (unbounded cache)
+            while len(self._engines) >= self.MAX_ENGINES:
+                self._engines.pop(next(iter(self._engines))).close()
             extra = {} if _BACKEND_FOR_TESTS is None else {"backend_cls": _BACKEND_FOR_TESTS}
-            self._engines[key] = self.eng.Engine(choice, self.boxsize, precision,
-                                                 device=self.device, group=self.group,
-                                                 fft_precision=self.fft_precision,
-                                                 accum_precision=self.accum_precision, **extra)
-        return self._engines[key]
+            if self.contraction is not None:
+                extra["contraction"] = self.contraction
+            e = self.eng.Engine(choice, self.boxsize, precision, device=self.device, group=self.group,
+                                fft_precision=self.fft_precision, accum_precision=self.accum_precision,
+                                **extra)
+        self._engines[key] = e
+        return e
 
     def compensation_tables(self, engine, comp):
         if comp is None:
@@ -108,20 +120,20 @@ _SHARED = {}            # (nmesh, box, grid, device, group, fft, accum) -> [sess
 _SHARED_MAX = 4
 
 
-def _acquire_session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype):
+def _acquire_session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype, contraction=None):
     """Sessions (cuFFT plans, contraction schedules, scratch) are shared between
     FFTBispectrum objects with the same geometry: a pipeline over many snapshots pays for
     plan creation once.  `clear_cache()` releases them."""
     key = (int(nmesh), tuple(np.asarray(boxsize, dtype=np.float64).tolist()), str(grid), str(device),
            id(group) if group is not None else None,
            None if fft_dtype is None else np.dtype(fft_dtype).name,
-           None if accum_dtype is None else np.dtype(accum_dtype).name)
+           None if accum_dtype is None else np.dtype(accum_dtype).name, contraction)
     ent = _SHARED.get(key)
     if ent is None:
         if len(_SHARED) >= _SHARED_MAX:          # drop idle sessions, oldest first
             for k in [k for k, v in _SHARED.items() if v[1] <= 0][:len(_SHARED) - _SHARED_MAX + 1]:
                 _SHARED.pop(k)[0].close()
-        ent = [_Session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype), 0]
+        ent = [_Session(nmesh, boxsize, grid, device, group, fft_dtype, accum_dtype, contraction), 0]
         _SHARED[key] = ent
     ent[1] += 1
     return key, ent[0]
@@ -133,8 +145,28 @@ def _release_session(key):
         ent[1] -= 1
 
 
+#: N_tri and k_mean depend on (Nmesh, BoxSize, bins, triangles) only, not on any mesh: the reference
+#: computes them once per binning and keeps them in a file (step 1 of its workflow, usage.md:27-37).
+#: Here the last few are kept in memory for the whole process, shared by every FFTBispectrum.
+_GRID_CACHE = {}
+_GRID_CACHE_MAX = 8
+_GRID_CACHE_ON = True
+
+
+def set_gridinfo_cache(enabled):
+    """Switch the process-wide cache of (N_tri, k_mean) results on or off (benchmarks switch it
+    off so that every step recomputes the normalisation); returns the previous setting."""
+    global _GRID_CACHE_ON
+    old = _GRID_CACHE_ON
+    _GRID_CACHE_ON = bool(enabled)
+    if not _GRID_CACHE_ON:
+        _GRID_CACHE.clear()
+    return old
+
+
 def clear_cache():
     """Destroy every cached session (plans, schedules, scratch buffers) that is not in use."""
+    _GRID_CACHE.clear()
     for k in [k for k, v in _SHARED.items() if v[1] <= 0]:
         _SHARED.pop(k)[0].close()
     for s in list(_sessions.values()):
@@ -186,20 +218,20 @@ class _Measurer:
     """Shared implementation behind the class methods and the module functions."""
 
     def __init__(self, meshes, grid="auto", compute_dtype=None, device=None, group=None,
-                 fft_dtype=None, accum_dtype=None):
+                 fft_dtype=None, accum_dtype=None, contraction=None):
         first = meshes[0]
         self.meshes = meshes
         self.nmesh = int(first.attrs["Nmesh"][0])
         self.boxsize = np.asarray(first.attrs["BoxSize"], dtype=np.float64)
         self._session_key, self.session = _acquire_session(self.nmesh, self.boxsize, grid, device,
-                                                           group, fft_dtype, accum_dtype)
+                                                           group, fft_dtype, accum_dtype, contraction)
+        self.last_schedule = None       # 'tensor' | 'tile' | 'stream': what the last data measurement ran
         if compute_dtype is None:
             # the reference computes in the mesh's own dtype (f4 meshes -> f4 fields)
             self.precision = F32 if all(_mesh_dtype_code(m) == F32 for m in meshes) else F64
         else:
             self.precision = F32 if np.dtype(compute_dtype) == np.float32 else F64
         self._cubes = {}
-        self._grid_cache = {}
 
     def release(self):
         """Drop this object's spectra; the shared session stays cached for the next object."""
@@ -239,6 +271,7 @@ class _Measurer:
         edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
         e = self.session.engine(edges[:, 1].max(), self.precision)
         sums = self.session.eng.measure_triangle_sums(e, self.cubes(e), edges, triples)
+        self.last_schedule = e.last_schedule
         return sums * self.volume() ** 2
 
     def gridinfo(self, edges, triples):
@@ -249,12 +282,17 @@ class _Measurer:
         # The result is mesh independent, so it is cached per binning (the reference caches it
         # in a file: step 1 of its 3-step workflow, usage.md:27-37).
         triples = np.ascontiguousarray(np.asarray(triples, dtype=np.int64).reshape(-1, 3))
-        key = (edges.tobytes(), triples.tobytes())
-        if key not in self._grid_cache:
+        key = (self.nmesh, tuple(self.boxsize.tolist()), edges.tobytes(), triples.tobytes())
+        hit = _GRID_CACHE.pop(key, None) if _GRID_CACHE_ON else None
+        if hit is None:
             e = self.session.engine(edges[:, 1].max(), F64,
                                     policy="auto" if self.session.grid_policy == "full" else None)
-            self._grid_cache = {key: self.session.eng.measure_grid_sums(e, edges, triples)}
-        ntri, kmean = self._grid_cache[key]
+            hit = self.session.eng.measure_grid_sums(e, edges, triples)
+        if _GRID_CACHE_ON:
+            while len(_GRID_CACHE) >= _GRID_CACHE_MAX:
+                _GRID_CACHE.pop(next(iter(_GRID_CACHE)))
+            _GRID_CACHE[key] = hit
+        ntri, kmean = hit
         return ntri.copy(), kmean.copy()
 
 
@@ -515,29 +553,39 @@ def downsample_mesh(mesh, Nmesh_new, device=None):
 
 
 def combine_gridinfo_and_unnormalized(bin_info, b_vals, k_max=np.inf, tol=0.01):
-    """B = B_unnorm / N_tri, the 12-column table of the reference's step 3
-    (scripts/process/process_fast_bs_measurement.py:37-82): truncate at the first
-    k1_min above ``k_max``, check index and edge agreement, divide."""
-    bin_info = np.atleast_2d(np.asarray(bin_info, dtype=np.float64))
-    b_vals = np.atleast_2d(np.asarray(b_vals, dtype=np.float64))
-    k1min = bin_info[:, 4]
-    if k1min[-1] > k_max:
-        i_from_k = int(np.where(k1min == k1min[k1min > k_max][0])[0][0]) - 1
-    else:
-        i_from_k = len(k1min)
-    i_max = min(len(bin_info), len(b_vals), i_from_k)
-    out = np.zeros((i_max, 12))
-    for i in range(i_max):
-        if bin_info[i, 0] != b_vals[i, 0]:
-            raise ValueError("Bin index mismatch between bin_info and B files: line %d: %d vs %d"
-                             % (i, bin_info[i, 0], b_vals[i, 0]))
-        for j in range(6):
-            if np.abs((bin_info[i, 4 + j] - b_vals[i, 1 + j]) / bin_info[i, 4 + j]) > tol:
-                raise ValueError("Bin bound mismatch between bin_info and B files: line %d: %e vs %e"
-                                 % (i, bin_info[i, 4 + j], b_vals[i, 1 + j]))
-        out[i, 0:10] = bin_info[i, 0:10]
-        out[i, 10] = b_vals[i, 7] / bin_info[i, 10]
-        out[i, 11] = bin_info[i, 10]
+    """Step 3 of the reference workflow (scripts/process/process_fast_bs_measurement.py:37-82):
+    join the grid-info table (index, three k_means, six edges, N_tri) with the unnormalised-B
+    table (index, six edges, B) into the 12-column table (index, k_means, edges, B/N_tri, N_tri).
+    Rows are kept up to, but not including, the row before the first whose lower k1 edge exceeds
+    ``k_max`` (the reference's cut); the two tables must agree on the triangle index and, to the
+    relative tolerance ``tol``, on every bin edge."""
+    info = np.atleast_2d(np.asarray(bin_info, dtype=np.float64))
+    bvals = np.atleast_2d(np.asarray(b_vals, dtype=np.float64))
+    k1_lo = info[:, 4]
+    n_keep = len(info)
+    above = np.flatnonzero(k1_lo > k_max)
+    if k1_lo[-1] > k_max and len(above):
+        # first row of the first k1 bin above k_max, minus one (process_fast_bs_measurement.py:41-51)
+        n_keep = int(np.flatnonzero(k1_lo == k1_lo[above[0]])[0]) - 1
+    n_keep = max(0, min(n_keep, len(bvals)))
+    info, bvals = info[:n_keep], bvals[:n_keep]
+    bad_index = np.flatnonzero(info[:, 0] != bvals[:, 0])
+    if len(bad_index):
+        i = int(bad_index[0])
+        raise ValueError("Bin index mismatch between bin_info and B files: line %d: %d vs %d"
+                         % (i, info[i, 0], bvals[i, 0]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs((info[:, 4:10] - bvals[:, 1:7]) / info[:, 4:10])
+    bad_edge = np.argwhere(rel > tol)
+    if len(bad_edge):
+        i, j = (int(v) for v in bad_edge[0])
+        raise ValueError("Bin bound mismatch between bin_info and B files: line %d: %e vs %e"
+                         % (i, info[i, 4 + j], bvals[i, 1 + j]))
+    out = np.zeros((n_keep, 12))
+    out[:, 0:10] = info[:, 0:10]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out[:, 10] = bvals[:, 7] / info[:, 10]
+    out[:, 11] = info[:, 10]
     return out
 
 
@@ -552,7 +600,10 @@ class FFTBispectrum:
     ``engine.choose_grid``), ``compute_dtype`` (storage dtype of the shell fields;
     default: the mesh dtype, as the reference computes), ``fft_dtype`` (precision of
     the inverse transforms, default float64), ``accum_dtype`` (precision of the triple
-    products and per-tile sums, default = compute_dtype), ``device`` and ``group``
+    products and per-tile sums, default = compute_dtype), ``contraction`` ('tensor': tcgen05
+    3xTF32 contraction for dense float32 lists, the default; 'fp32': exact round-to-nearest
+    products on the FP32 pipe -- after a data measurement ``attrs['contraction_path']`` says
+    which kernel ran: 'tensor', 'tile' or 'stream'), ``device`` and ``group``
     (torch.distributed process group; every rank must make the same calls).
     """
 
@@ -563,7 +614,7 @@ class FFTBispectrum:
                  pos_units_mpcoverh=1.0, k_edges=None, second=None, third=None,
                  triangle_type="all", isos_mult=0, isos_tol=0.1, squeezed_bin_index=0,
                  for_grid_info_only=False, *, grid="auto", compute_dtype=None, fft_dtype=None,
-                 accum_dtype=None, device=None, group=None):
+                 accum_dtype=None, contraction=None, device=None, group=None):
         self.first = cast_source(source, Nmesh=Nmesh, BoxSize=BoxSize)
         self.mesh = self.first
         self.second = None
@@ -617,8 +668,11 @@ class FFTBispectrum:
             self.k_indices = gen(True)
 
         self.b = None
+        if contraction not in (None, "tensor", "fp32"):
+            raise ValueError("contraction must be 'tensor' or 'fp32'")
         self._engine_opts = dict(grid=grid, compute_dtype=compute_dtype, device=device, group=group,
-                                 fft_dtype=fft_dtype, accum_dtype=accum_dtype)
+                                 fft_dtype=fft_dtype, accum_dtype=accum_dtype, contraction=contraction)
+        self.attrs["contraction"] = contraction      # requested; attrs['contraction_path'] = what ran
         self._measurer = None
         if not for_grid_info_only:
             self._paint_meshes()
@@ -716,6 +770,7 @@ class FFTBispectrum:
                 if not self.attrs.get("painted", False):
                     self._paint_meshes()
                 B = meas.unnormalized(edges, triples)
+                self.attrs["contraction_path"] = meas.last_schedule
                 if meas_type == "full":
                     with np.errstate(divide="ignore", invalid="ignore"):
                         B = B / ntri
@@ -754,6 +809,7 @@ class FFTBispectrum:
             if not self.attrs.get("painted", False):
                 self._paint_meshes()
             B = self._meas().unnormalized(edges, triples) * float(self.attrs["pos_units_mpcoverh"]) ** 6.0
+            self.attrs["contraction_path"] = self._meas().last_schedule
         new = self._store(idx, tri, np.zeros((T, 3)), B, np.zeros(T))
         if out_file is not None and self._rank0() and T:
             with open(out_file, "a") as f:

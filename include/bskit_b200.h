@@ -105,6 +105,10 @@ int bsk_plan_destroy(bsk_plan* plan);
 int bsk_plan_info(const bsk_plan* plan, bsk_info* out);
 int bsk_set_compensation(bsk_plan* plan, const double* comp_x, const double* comp_y,
                          const double* comp_z);
+/* Enqueue every later call of this plan (kernels and cuFFT plans) on `cuda_stream`.  The host calls
+ * it with its current stream before each stage, so a plan built under one stream can be used under
+ * another (the reference has no streams: every pmesh call is synchronous). */
+int bsk_plan_set_stream(bsk_plan* plan, void* cuda_stream);
 
 /* Forward transform of this rank's x-slab (replaces mesh.paint(mode='complex'),
  * main.py:1608-1621, plus the queued compensation action).  Runs in float64, in chunks
@@ -150,16 +154,19 @@ int bsk_cplan_info(const bsk_cplan* cp, int64_t out[4]); /* nblocks, split, roun
 
 /* Contraction path of a schedule.  path 0 (default): FP32-pipe tile kernel (packed FFMA2, exact
  * round-to-nearest products).  path 1: tcgen05 tensor cores, 3xTF32 operands with the pair
- * products written to TMEM, accumulators drained every 128 cells (relative error ~8e-7 instead of
- * ~5e-8; the Python host selects it by default).  Path 1 is used only when the list is eligible: float32 fields and products, one job
- * with zero offsets, at most 40 rows, at least 256 triangles, ncells a multiple of 128;
- * otherwise bsk_contract runs path 0.  bsk_cplan_path: out = {tensor-core units of the
- * schedule (0: not eligible), requested path, path the last bsk_contract call ran}. */
+ * products written to TMEM, accumulators drained every 128 cells (relative error ~8e-7 of the
+ * largest sums instead of ~5e-8; the Python host selects it by default).  Path 1 is used only when
+ * the call is eligible: float32 fields and products, one job with zero offsets, at least 256
+ * triangles, ncells a multiple of 128; lists that do not fit one launch (more than 40 column rows,
+ * 96 accumulator columns per team or 120 raw rows: S = 80 bins, two- and three-field lists) run as
+ * several passes.  Otherwise bsk_contract runs path 0.  bsk_cplan_path: out = {tensor-core units
+ * of the schedule (0: not eligible), requested path, path the last bsk_contract call ran}. */
 int bsk_cplan_set_path(bsk_cplan* cp, int path);
 /* Host only (no device needed): the tensor-core schedule bsk_cplan_create builds for a list.
- * out = {128-row units (0: list not eligible), distinct accumulator slots read by the triangles
- * (== ntri), sum of the units' accumulator columns, pair rows generated, all slots in range,
- * slots per CTA}. */
+ * out = {128-row units over all passes (0: list not eligible), distinct accumulator slots read by
+ * the triangles (== number of distinct sorted triangles; negative if two different triangles
+ * share a slot), sum of the units' accumulator columns, passes (kernel launches), all slots in
+ * range, sum over units of max(11, columns/2) (MMA cycles per 8 cells and operand term)}. */
 int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6]);
 int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]);
 
@@ -177,6 +184,16 @@ int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]);
 int bsk_contract(bsk_cplan* cp, const void* const* row_ptrs, int precision, int accum_precision,
                  int64_t ncells, int njobs, const int32_t* job_off, double* sums,
                  void* cuda_stream);
+
+/* Fold of even fields for the normalisation (main.py:2006-2061).  n_i and kappa_i depend on |k|
+ * only, so they are even in every axis and sum_x over the grid equals the sum over [0, M/2] per
+ * mirrored axis with weight prod_axis (1 on the planes 0 and M/2, else 2).  Writes, for each of
+ * the `nrows` contiguous fields [mxl][M][M], the cells [0,nx) x [0,M/2] x [0,M/2] scaled by the
+ * cube root of that weight (so the weight lands in the triple product), rows zero-padded to
+ * ncell_out.  fold_x = 1 (whole grid local, nx = M/2+1) folds all three axes, fold_x = 0
+ * (x-slab of a multi-GPU run, nx = mxl) folds y and z only. */
+int bsk_fold_even(const void* fields, int precision, int nrows, int neval, int mxl, int fold_x, void* out,
+                  int64_t ncell_out, void* cuda_stream);
 
 /* Sparse triangle lists (equilateral / squeezed / isosceles, T ~ S: every triangle touches
  * <= 3 fields): one coalesced streaming pass per triangle straight from HBM,

@@ -14,7 +14,7 @@ class FakeBackend:
     name = "numpy-test-double"
 
     def __init__(self, grid, boxsize, precision, world, rank, device, max_shells,
-                 fft_precision=None, accum_precision=None, no_prune=False):
+                 fft_precision=None, accum_precision=None, no_prune=False, contraction=None):
         self.grid, self.world, self.rank = grid, world, rank
         n, m = grid.nmesh, grid.neval
         kxy = n if grid.full else 2 * grid.ncrop + 1
