@@ -158,11 +158,20 @@ __device__ __forceinline__ void pin8(float2 (&v)[4]) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// not volatile: the compiler may hoist and batch these loads
+// Shared-memory load that the compiler may hoist, batch and reorder freely (no volatile, no memory
+// clobber).  The tile must not change while such loads are in flight, and the address must depend
+// on order_token() of the wait that made the tile visible.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
-  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+// an opaque zero produced after everything before it (volatile + memory clobber): adding it to an
+// address keeps the loads through that address behind the wait
+__device__ __forceinline__ uint32_t order_token() {
+  uint32_t t;
+  asm volatile("mov.u32 %0, 0;" : "=r"(t)::"memory");
+  return t;
 }
 // L2 policies: the fields stream through once per pass (evict first), the float64 partials are
 // re-read by every flush (evict last) -- keeps the flushes out of DRAM
@@ -310,7 +319,7 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     const int buf = it % p.nbuf;
     tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it / p.nbuf) & 1u);
     tick(t_raw);
-    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb);
+    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb) + order_token();
     {   // this thread's share of the tile's operand images (the MMAs of tile it-2 have released them)
       const int bbuf = it & 1;
       tc_wait(bars + (B_EMPTY + bbuf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);

@@ -158,7 +158,7 @@ inline bool place_pass(const std::vector<std::pair<int, int>>& cls,
       if (pl.pos[w][j] >= 0) return pcs[pl.pos[w][j]].host;
     return -1;
   };
-  for (int attempt = 0; attempt < 48; ++attempt) {
+  for (int attempt = 0; attempt < 48 || (!found && attempt < 400); ++attempt) {
     // orientation: which group hosts each class (diagonal classes host themselves)
     std::vector<Piece> pcs;
     for (size_t i = 0; i < cls.size(); ++i) {
@@ -481,7 +481,12 @@ inline bool build_schedule(int ntri, const int32_t* rows, int nrows, Schedule& o
   const bool oka = build_schedule_mode(ntri, rows, nrows, false, a);
   const bool okb = build_schedule_mode(ntri, rows, nrows, true, b);
   if (!oka && !okb) return false;
-  out = (okb && (!oka || b.est_cycles < a.est_cycles)) ? std::move(b) : std::move(a);
+  bool pick_b = okb && (!oka || b.est_cycles < a.est_cycles);
+  if (const char* force = getenv("BSK_TC_COVER")) {       // A/B knob: 0 = two smallest rows, 1 = class cover
+    if (force[0] == '0' && oka) pick_b = false;
+    if (force[0] == '1' && okb) pick_b = true;
+  }
+  out = pick_b ? std::move(b) : std::move(a);
   return true;
 }
 
