@@ -50,7 +50,10 @@ namespace tc {
 constexpr int CH = 32;            // cells per chunk = K extent of one unit
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
-constexpr int WIN = 4;            // chunks accumulated in TMEM before a drain
+#ifndef BSK_TC_WIN
+#define BSK_TC_WIN 4
+#endif
+constexpr int WIN = BSK_TC_WIN;   // chunks accumulated in TMEM before a drain
 constexpr int MAXCOL = 40;        // column rows per pass (N of an MMA <= 40)
 constexpr int MAXRAW = 120;       // raw rows per pass (8-row groups: 15)
 constexpr int NTEAMS = 2;
@@ -64,7 +67,7 @@ constexpr int NTHREADS = 2 * NGEN + 128;    // generator teams + one drain warpg
 constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
 // 640 threads are launched with 96 registers each; setmaxnreg then moves registers from the
 // auxiliary warps to the drain warpgroups, which hold the second-level accumulators
-constexpr int REGS_GEN = 96, REGS_DRAIN = 120, REGS_AUX = 40;
+constexpr int REGS_GEN = 96, REGS_DRAIN = 120, REGS_AUX = 48;
 static_assert(NGEN * (REGS_GEN + REGS_DRAIN) + 128 * REGS_AUX <= NTHREADS * 96, "register split");
 // accumulator columns per team: 12 blocks of 8 columns, handed out to the team's units by the
 // host (Params::ublk0); a unit of width ncol uses ncol/8 consecutive blocks
@@ -442,25 +445,25 @@ __device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint3
 #define BSK_TC_ZERO(K, M) _Pragma("unroll") for (int c = 0; c < 4; ++c) acc.M[c] = make_float2(0.f, 0.f);
   BSK_TC_FOR_BLOCKS(BSK_TC_ZERO)
 #undef BSK_TC_ZERO
+  // few live scalars next to the 96 accumulators (120 registers): the units' first block and block
+  // count are packed into one word (8 bits per unit), the window parities into another
   const int my_nu = p.nu[team];
-  int blk0[UPT], nblk[UPT];
-  int used = 0;
+  uint32_t cfg = 0, used = 0;
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
-    blk0[j] = p.ublk0[team * UPT + j];
-    nblk[j] = j < my_nu ? p.uncol[team * UPT + j] / 8 : 0;
-    used = max(used, blk0[j] + nblk[j]);
+    const uint32_t b0 = (uint32_t)p.ublk0[team * UPT + j], nb = j < my_nu ? (uint32_t)p.uncol[team * UPT + j] / 8u : 0u;
+    cfg |= (b0 | (nb << 4)) << (8 * j);
+    used = max(used, b0 + nb);
   }
   const uint32_t d_base = tbase + ((uint32_t)(q * 32) << 16) + TM_D + (uint32_t)team * TEAMCOLS;
-  const uint32_t bar_full = bars + (D_FULL + team * UPT) * 8, bar_empty = bars + (D_EMPTY + team * UPT) * 8;
-  double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * ((int64_t)TEAMCOLS * 128) + q * 32 + lane;
-  const uint64_t pol = policy_evict_last();
+  const uint32_t bar_full = bars + (D_FULL + team * UPT) * 8;     // D_EMPTY follows NUNITS barriers later
+  uint32_t parity = 0;     // bit j: parity of unit j's next window
   int since_flush = 0;
   long long d_wait = 0, d_work = 0;
-  uint32_t nwin[UPT];
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) nwin[j] = 0;
+  uint32_t n0 = 0;
   auto flush = [&]() {
+    double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * ((int64_t)TEAMCOLS * 128) + q * 32 + lane;
+    const uint64_t pol = policy_evict_last();
 #define BSK_TC_FLUSH(K, M)                                                                         \
   if (K < used) {                                                                                  \
     _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                \
@@ -472,29 +475,33 @@ __device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint3
     BSK_TC_FOR_BLOCKS(BSK_TC_FLUSH)
 #undef BSK_TC_FLUSH
   };
-  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t gtot = (uint32_t)(my_tiles * NCH);
-#pragma unroll 1
-  for (uint32_t g = 0; g < gtot; ++g) {
-#pragma unroll
-    for (int j = 0; j < UPT; ++j) {
-      if (nblk[j] > 0 && win_closes(g, team * UPT + j, gtot)) {
-        drain_unit(acc, blk0[j], nblk[j], d_base + blk0[j] * 8, bar_full + j * 8, bar_empty + j * 8, nwin[j] & 1u, lane,
-                   d_wait, d_work);
-        ++nwin[j];
-      }
+  const uint32_t gtot = (uint32_t)((p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) * NCH);
+  auto drain_j = [&](uint32_t j) {
+    const uint32_t nb = (cfg >> (8 * j + 4)) & 15u, b0 = (cfg >> (8 * j)) & 15u;
+    if (nb > 0) {
+      drain_unit(acc, (int)b0, (int)nb, d_base + b0 * 8, bar_full + j * 8, bar_full + (NUNITS + j) * 8, (parity >> j) & 1u,
+                 lane, d_wait, d_work);
+      parity ^= 1u << j;
+      if (j == 0) ++n0;
     }
+  };
+#pragma unroll 1
+  for (uint32_t g = 0; g + 1 < gtot; ++g) {
+    // the units that close their window after chunk g: (g + team * UPT + j) % WIN == WIN - 1
+    for (uint32_t j = (2 * WIN - 1 - (g + (uint32_t)team * UPT) % WIN) % WIN; j < UPT; j += WIN) drain_j(j);
     if (++since_flush >= p.flush_chunks) {
       flush();
       since_flush = 0;
     }
   }
+  if (gtot > 0)      // after the last chunk every unit closes
+    for (uint32_t j = 0; j < UPT; ++j) drain_j(j);
   flush();
   if constexpr (PROF) {
     if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
       p.prof[(2 * NTEAMS + team) * 8 + 0] = d_wait;
       p.prof[(2 * NTEAMS + team) * 8 + 1] = d_work;
-      p.prof[(2 * NTEAMS + team) * 8 + 2] = nwin[0];
+      p.prof[(2 * NTEAMS + team) * 8 + 2] = n0;
     }
   }
 }
