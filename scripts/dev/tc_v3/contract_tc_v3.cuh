@@ -10,78 +10,100 @@
 // tcgen05.st and never touch shared memory; B = the fields, converted once per tile into K-major
 // core matrices (hi and lo images).
 //
-// What bounds the kernel is shared-memory bandwidth: every pair row needs the cells of its two
-// fields in the registers of the lane that owns the row.  Round 1 read both rows per lane and
-// unit (8 wavefronts per 4 cells and warp).  Measured (scripts/dev/lds_probe.cu,
+// What bounds the kernel is the generation of the pair products on the CUDA cores (per 8 cells
+// and lane: 2 shared-memory loads, 4 packed multiplies, 16 integer operations for the
+// round-to-nearest tf32 split, 4 packed FMAs, 2 TMEM stores).  ncu on the round-1 kernel and on
+// the first round-2 version (profiles/r2_tc_contract_history.md): a generator warp issues only
+// ~0.3 instructions per cycle (dependent chains, fixed-latency stalls), so with two generator
+// warps per SM sub-partition the SM idles.  This version therefore runs FOUR generator warps per
+// sub-partition (16 warps, four teams).  The registers for them come from the drain warps: the
+// second-level accumulators live in TMEM (D2) instead of 96 registers per drain thread.
+//
+// Shared-memory traffic (round 1: 69 % of the wavefront peak).  Measured (scripts/dev/lds_probe.cu,
 // profiles/r2_lds_probe.txt): a warp-wide LDS.128 costs 4 cycles when the lanes read 32 different
-// 16-byte chunks, 2 cycles when every even/odd lane pair reads the same chunk.  The layout here:
-//   * rows are handled in groups of 8; a generator warp "hosts" one group for the whole chunk:
-//     lane l keeps row 8*host + (l & 7) of the chunk in registers (32 cells) across the units;
+// 16-byte chunks, 2 cycles when every even/odd lane pair reads the same chunk.  Layout:
+//   * rows are handled in groups of 8; a generator warp "hosts" one group for a chunk: lane l keeps
+//     row 8*host + (l & 7) of the chunk in registers (32 cells) across the units that share it;
 //   * in unit j the warp meets a partner group: lane pair k = l >> 1 reads row
 //     8*part + ((k & 7) + s) & 7, s = 2*piece + (k >> 3) -- lane pairs share the chunk they read
 //     (2-cycle LDS), the 8 pairs of a half warp read 8 consecutive rows (distinct banks), and
 //     two such "pieces" cover all 64 pairs of two groups.
-// Shared-memory reads per 4 cells, warp and unit drop from 8 wavefronts to 2 (+ 4/U for the
-// resident row, U = units that share the host group).
 //
 // Numerics.  3xTF32: P = F_a*F_b (fp32, RN) is split P = P_hi + P_lo, F_c = C_hi + C_lo with
 // 11-bit pieces (hi parts rounded to nearest), D += P_lo*C_hi + P_hi*C_lo + P_hi*C_hi.  The
-// tensor core truncates its fp32 accumulator (profiles/r1_tensor_core_rounding_probe.txt), so an
-// accumulator lives in TMEM for one window of WIN chunks only; it is then drained into fp32
-// registers (round-to-nearest adds), flushed into float64 partials every flush_chunks chunks.
-// Window ends are staggered over the units so the TMEM reads (64 B/cycle/SM) spread evenly.
+// tensor core truncates its fp32 accumulator (profiles/r1_tensor_core_rounding_probe.txt), so a
+// first-level accumulator (D1, TMEM) lives for one window of WIN chunks only; the drain warps add
+// it to the second-level accumulator (D2, TMEM, read-modify-write through registers, round to
+// nearest) and D2 is flushed into float64 partials every flush_chunks chunks.  Window ends are
+// staggered over the units so the TMEM traffic spreads evenly.
 //
-// Roles (640 threads, one CTA per SM, persistent over tiles of 128 cells; setmaxnreg 96/120/40):
-//   2 x 4 warps  generator teams: warp q of a team owns TMEM lanes [32q, 32q+32)
-//   2 x 4 warps  drain warpgroups, one per team: second-level accumulators of the team's units
-//                (96 columns per team, handed out to the units in blocks of 8)
+// Roles (896 threads, one CTA per SM, persistent over tiles of 128 cells; setmaxnreg 88/40/48):
+//   4 x 4 warps  generator teams: warp q of a team owns TMEM lanes [32q, 32q+32); they also convert
+//                the raw tile into the operand images at the start of a tile
+//   2 x 4 warps  drain warps: unit u belongs to drain group u % 2
 //   1 warp       TMA producer (raw [row][cell] tiles, cp.async.bulk + mbarrier), up to 3 tiles ahead
-//   2 warps      MMA issuers, one per team (one elected lane each)
-//   (the generators also convert the raw tile into the operand images at the start of a tile)
+//   2 warps      MMA issuers, each for two teams (one elected lane each)
 //
-// A launch processes one "pass": <= 8 units with <= 96 accumulator columns per team, over a
-// window of <= 40 column rows and <= MAXRAW raw rows.  Lists that need more (S = 80 bins, 2-3
-// field cross lists) run as several passes (host schedule: contract.cu, build_tc_schedule_host).
+// A launch processes one "pass": <= 16 units with <= 128 accumulator columns in total, over a
+// window of <= 40 column rows and <= MAXRAW raw rows.  Lists that need more (S = 40 all triangles:
+// two passes; S = 80; 2-3 field cross lists) run as several passes (host schedule: tc_schedule.h).
 #pragma once
 
 namespace bsk {
 namespace tc {
 
-constexpr int CH = 32;            // cells per chunk = K extent of one unit
+constexpr int CH = 32;            // cells per chunk: the resident row is loaded once per chunk
+#ifndef BSK_TC_HC
+#define BSK_TC_HC 16
+#endif
+constexpr int HC = BSK_TC_HC;     // cells per hand-over: one A buffer
+constexpr int NABUF = 32 / HC;    // A buffers per team (hi HC + lo HC columns each; 64 TMEM columns per team)
+constexpr bool DEFER = NABUF > 1; // hand a half unit over only after the next one's first products are computed
 constexpr int TL = 128;           // cells per tile
 constexpr int NCH = TL / CH;
 #ifndef BSK_TC_WIN
 #define BSK_TC_WIN 4
 #endif
-constexpr int WIN = BSK_TC_WIN;   // chunks accumulated in TMEM before a drain
+constexpr int WIN = BSK_TC_WIN;   // chunks accumulated in D1 before a drain
 constexpr int MAXCOL = 40;        // column rows per pass (N of an MMA <= 40)
 constexpr int MAXRAW = 120;       // raw rows per pass (8-row groups: 15)
-constexpr int NTEAMS = 2;
-constexpr int UPT = 4;            // units per team
+constexpr int NTEAMS = 4;
+#ifndef BSK_TC_UPT
+#define BSK_TC_UPT 4
+#endif
+constexpr int UPT = BSK_TC_UPT;   // units per team
 constexpr int NUNITS = NTEAMS * UPT;
 constexpr int NGEN = NTEAMS * 128;
-constexpr int NTHREADS = 2 * NGEN + 128;    // generator teams + one drain warpgroup per team + 4 auxiliary warps
+constexpr int NDRAIN = 256;
+constexpr int NISSUE = 2;         // MMA issuer warps; issuer i serves teams i, i + NISSUE, ...
+constexpr int NTHREADS = NGEN + NDRAIN + 128;
 #ifndef BSK_TC_PROF
 #define BSK_TC_PROF 0
 #endif
 constexpr bool PROF = BSK_TC_PROF;   // cycle counters per phase (block 0), see Params::prof
-// 640 threads are launched with 96 registers each; setmaxnreg then moves registers from the
-// auxiliary warps to the drain warpgroups, which hold the second-level accumulators
-constexpr int REGS_GEN = 96, REGS_DRAIN = 120, REGS_AUX = 48;
-static_assert(NGEN * (REGS_GEN + REGS_DRAIN) + 128 * REGS_AUX <= NTHREADS * 96, "register split");
-// accumulator columns per team: 12 blocks of 8 columns, handed out to the team's units by the
-// host (Params::ublk0); a unit of width ncol uses ncol/8 consecutive blocks
-constexpr int TEAMCOLS = 96, NBLK = TEAMCOLS / 8;
-constexpr int CAPTOT = NTEAMS * TEAMCOLS;   // 192
-// TMEM columns: the teams' accumulators and two A buffers (hi 32 + lo 32 columns) per team
-constexpr int TM_D = 0, TM_A = 256;
-static_assert(CAPTOT <= TM_A && TM_A + NTEAMS * 2 * 64 <= 512, "TMEM budget");
+#ifndef BSK_TC_SLEEP
+#define BSK_TC_SLEEP 256
+#endif
+#ifndef BSK_TC_EXP
+#define BSK_TC_EXP 0
+#endif
+constexpr int EXP = BSK_TC_EXP;      // timing experiments (wrong results), bit mask: 1 no MMAs, 2 no TMEM stores, 4 no partner loads, 8 no split, 16 resident row loaded once per tile, 32 no image conversion
+// 896 threads are launched with 72 registers each; setmaxnreg then moves registers from the drain
+// and auxiliary warps to the generators
+constexpr int REGS_LAUNCH = 72, REGS_GEN = 88, REGS_DRAIN = 40, REGS_AUX = 48;
+static_assert(NGEN * REGS_GEN + NDRAIN * REGS_DRAIN + 128 * REGS_AUX <= NTHREADS * REGS_LAUNCH, "register split");
+// TMEM columns: first-level accumulators D1, second-level accumulators D2 (same layout), two A
+// buffers (hi 16 + lo 16 columns) per team
+constexpr int DCOLS = 128;
+constexpr int TM_D1 = 0, TM_D2 = DCOLS, TM_A = 2 * DCOLS;
+static_assert(TM_A + NTEAMS * NABUF * 2 * HC <= 512, "TMEM budget");
+static_assert(NTEAMS * NABUF <= 15, "named barriers");
 
 constexpr int RAW_STRIDE = TL * 4 + 16;            // bytes; 8 consecutive rows tile the 32 banks
 constexpr int MAXRAWBUF = 4;                       // raw tiles in flight (as many as fit next to the images)
 constexpr int BIMG_BYTES = (TL / 4) * (MAXCOL / 8) * 128;   // one hi or lo image of a tile
 constexpr int OFF_BAR = 0;
-constexpr int OFF_BIMG = 512;                      // [buf][hi|lo]
+constexpr int OFF_BIMG = 1024;                     // [buf][hi|lo]
 constexpr int OFF_RAW = OFF_BIMG + 4 * BIMG_BYTES;
 constexpr int SMEM_MAX = 227 * 1024;
 static_assert(OFF_BIMG % 128 == 0 && OFF_RAW % 128 == 0, "operand images must be 128-byte aligned");
@@ -95,7 +117,7 @@ static_assert(raw_bufs(MAXRAW) >= 2, "shared memory");
 // barrier indices
 enum {
   RAW_FULL = 0, RAW_EMPTY = RAW_FULL + MAXRAWBUF, B_FULL = RAW_EMPTY + MAXRAWBUF, B_EMPTY = B_FULL + 2,
-  A_FULL = B_EMPTY + 2, A_EMPTY = A_FULL + 2 * NTEAMS, D_FULL = A_EMPTY + 2 * NTEAMS, D_EMPTY = D_FULL + NUNITS,
+  A_FULL = B_EMPTY + 2, A_EMPTY = A_FULL + NABUF * NTEAMS, D_FULL = A_EMPTY + NABUF * NTEAMS, D_EMPTY = D_FULL + NUNITS,
   NBAR = D_EMPTY + NUNITS
 };
 static_assert(NBAR * 8 + 8 <= OFF_BIMG, "barrier area");
@@ -111,9 +133,27 @@ __device__ __forceinline__ void tc_wait(uint32_t bar_addr, uint32_t parity) {
   }
   __trap();
 }
-// named (hardware) barriers for the generator -> MMA issuer hand-over: a hop costs ~16 cycles instead
-// of ~110 through an mbarrier (profiles/r2_sync_probe.txt).  id in [1, 15]; count = the team's 4 generator
-// warps + the issuer warp = 160 threads
+// wait of a warp that has slack (drain warps, TMA producer): back off between polls so that the
+// polling does not crowd the memory-I/O queue the generators' loads and barrier tests go through
+__device__ __forceinline__ void tc_wait_lazy(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(BSK_TC_SLEEP);
+  }
+  __trap();
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  return ok;
+}
+// named (hardware) barriers for the generator -> MMA issuer hand-over: far lower latency than an
+// mbarrier wake-up.  id in [1, 15]; count = 4 generator warps + the issuer warp = 160 threads
 __device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar_addr) {
@@ -149,6 +189,11 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint32_t des
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t addr, const float2 (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "f"(v[0].x), "f"(v[0].y),
+               "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y)
                : "memory");
 }
 // issue a TMEM load of 8 columns as four float2 (no wait)
@@ -201,7 +246,7 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src, u
       : "memory");
 }
 // float -> double conversion inside the asm statement: left to the compiler, the conversions of
-// all accumulators are hoisted in front of the reductions and double the register demand
+// many values are hoisted in front of the reductions and double the register demand
 __device__ __forceinline__ void red_add_f64_hint(double* addr, float v, uint64_t pol) {
   asm volatile("{\n.reg .f64 d;\ncvt.f64.f32 d, %1;\nred.global.add.L2::cache_hint.f64 [%0], d, %2;\n}\n" ::"l"(addr), "f"(v), "l"(pol)
                : "memory");
@@ -216,11 +261,11 @@ struct Params {
   int colslot[MAXCOL / 8];      // raw slot of the first row of each 8-column block
   int64_t ntiles;               // ncells / TL
   int nu[NTEAMS];               // units per team
-  int ucol0[NUNITS];            // [team * UPT + j]: first D column the unit needs (multiple of 8)
-  int uncol[NUNITS];            //                   number of columns (multiple of 8)
-  int ublk0[NUNITS];            //                   first accumulator block of the unit within its team
+  uint8_t ucol0[NUNITS];        // [team * UPT + j]: first image column the unit needs (multiple of 8)
+  uint8_t uncol[NUNITS];        //                   number of columns (multiple of 8, <= 40; 0: no such unit)
+  uint8_t udcol[NUNITS];        //                   first accumulator column (D1 / D2) of the unit
   const uint32_t* lane_tab;     // [team * UPT + j][128]: a_slot | b_slot << 8
-  double* partial;              // [cta][team][TEAMCOLS][128]
+  double* partial;              // [cta][DCOLS][128]
   int flush_chunks;
   long long* prof;              // PROF only
 };
@@ -233,10 +278,9 @@ __device__ __forceinline__ bool win_closes(uint32_t g, int u, uint32_t gtot) {
 }
 __device__ __forceinline__ bool win_opens(uint32_t g, int u) { return g == 0 || ((g + (uint32_t)u) % WIN) == 0; }
 
-// operand-image conversion, done by the 256 generator threads at the start of a tile (a separate
-// converter warp pair could not keep up once the generators got faster): raw fp32 -> tf32 hi
-// (round to nearest) + lo.  Thread gt owns column gt & 63 (if it exists) and the 4-cell groups
-// g = (gt >> 6) + 4k: 8 independent items per thread, 5 % of a tile's generator instructions.
+// operand-image conversion, done by the 512 generator threads at the start of a tile: raw fp32 ->
+// tf32 hi (round to nearest) + lo.  Thread gt owns column gt & 63 (if it exists) and the 4-cell
+// groups g = (gt >> 6) + 8k: 4 independent items per thread.
 __device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uint32_t img_hi, uint32_t img_lo, int gt,
                                               uint32_t col_slot) {
   const int l = gt & 63;
@@ -245,8 +289,8 @@ __device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uin
     const uint32_t row = raw + col_slot * RAW_STRIDE;
     const uint32_t o = (uint32_t)(l >> 3) * 128u + (uint32_t)(l & 7) * 16u;
 #pragma unroll
-    for (int k = 0; k < TL / 16; ++k) {
-      const uint32_t g = (uint32_t)(gt >> 6) + 4u * k;
+    for (int k = 0; k < TL / 4 / (NGEN / 64); ++k) {
+      const uint32_t g = (uint32_t)(gt >> 6) + (uint32_t)(NGEN / 64) * k;
       const float4 v = lds128(row + g * 16u);
       const float x[4] = {v.x, v.y, v.z, v.w};
       uint32_t h[4], lo[4];
@@ -263,16 +307,10 @@ __device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uin
 }
 
 // Generator team member; q = warp % 4 is the TMEM lane quarter.  Pure producer: writes the
-// 128 x 32 pair products (hi, lo) of one unit into one of the team's two A buffers.  The
-// hand-over of a unit (tcgen05.wait::st + arrive) is deferred until the first products of the next
-// unit are in registers, and the A buffer is probed (test_wait) before the loads are issued, so
-// neither latency is exposed; a warp without a piece in a unit only keeps the protocol going.
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar_addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
-  return ok;
-}
+// 128 x 16 pair products (hi, lo) of half a unit into one of the team's two A buffers.  The
+// hand-over (tcgen05.wait::st + arrive) is deferred until the first products of the next half are
+// in registers, and the A buffer is probed (test_wait) before the loads are issued; a warp
+// without a piece in a unit only keeps the protocol going.
 __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase,
                                           int team, int q, int lane) {
   const int my_nu = p.nu[team];
@@ -289,8 +327,7 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     idle[j] = __all_sync(0xffffffffu, e == none);
     reload[j] = j == 0 || __any_sync(0xffffffffu, ra_off[j] != ra_off[j - 1]);
   }
-  // the resident row must be (re)loaded in the first non-idle unit of a chunk
-  {
+  {   // the resident row must be (re)loaded in the first non-idle unit of a chunk
     bool have = false;
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {
@@ -302,10 +339,10 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
   const int gt = team * 128 + q * 32 + lane;
   const uint32_t col_slot = (gt & 63) < p.ncols ? (uint32_t)(p.colslot[(gt & 63) >> 3] + (gt & 7)) : 0u;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-  const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
-  const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
-  uint32_t n_gen = 0;     // units generated by this team so far
-  bool pending = false;   // the previous unit's stores have not been handed over yet
+  const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * (NABUF * 2 * HC);
+  const uint32_t bar_afull = bars + (A_FULL + team * NABUF) * 8, bar_aempty = bars + (A_EMPTY + team * NABUF) * 8;
+  uint32_t n_gen = 0;     // hand-overs (half units) generated by this team so far
+  bool pending = false;   // the previous half unit's stores have not been handed over yet
   uint32_t pending_ab = 0;
   long long t_raw = 0, t_gen = 0, t_aempty = 0, t_st = 0, t_mark = 0;
   auto tick = [&](long long& acc_t) {
@@ -315,7 +352,7 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     if (pending) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      nbar_arrive(1 + team * 2 + (int)pending_ab, 160);
+      nbar_arrive(1 + team * NABUF + (int)pending_ab, 160);
       pending = false;
     }
   };
@@ -324,14 +361,14 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = it % p.nbuf;
-    tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it / p.nbuf) & 1u);
-    tick(t_raw);
+    if (!(EXP & 128)) tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it / p.nbuf) & 1u);
     const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb) + order_token();
     {   // this thread's share of the tile's operand images (the MMAs of tile it-2 have released them)
       const int bbuf = it & 1;
       tc_wait(bars + (B_EMPTY + bbuf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      convert_share(p, raw, smem_u32(smem + OFF_BIMG + (bbuf * 2 + 0) * BIMG_BYTES),
-                    smem_u32(smem + OFF_BIMG + (bbuf * 2 + 1) * BIMG_BYTES), gt, col_slot);
+      if (!(EXP & 32))
+        convert_share(p, raw, smem_u32(smem + OFF_BIMG + (bbuf * 2 + 0) * BIMG_BYTES),
+                      smem_u32(smem + OFF_BIMG + (bbuf * 2 + 1) * BIMG_BYTES), gt, col_slot);
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + (B_FULL + bbuf) * 8);
       tick(t_raw);
@@ -343,51 +380,61 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j < my_nu) {
-          const uint32_t ab = n_gen & 1u;
-          const uint32_t a_tmem = a_tmem0 + ab * 64u;
-          const uint32_t ok = mbar_test(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
-          if (idle[j]) {
-            hand_over();
-            if (!ok) tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
-          } else {
-            if (reload[j]) {
+          if (!idle[j] && reload[j] && (!(EXP & 16) || c == 0)) {
 #pragma unroll
-              for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + ra_off[j] + v4 * 16);
-            }
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {   // 8 cells at a time
-              const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
-              const float4 a0 = own[2 * h], a1 = own[2 * h + 1];
-              const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-              const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 pr = __fmul2_rn(pa[i], pb[i]);
-                // hi = product rounded to nearest tf32 (11 bits): the low part is then sign-symmetric and
-                // at most 2^-12 |P|, so the tensor core's truncation of it costs 2^-23 instead of 2^-22
-                const float2 ph = make_float2(__uint_as_float((__float_as_uint(pr.x) + 0x1000u) & 0xFFFFE000u),
-                                              __uint_as_float((__float_as_uint(pr.y) + 0x1000u) & 0xFFFFE000u));
-                const float2 pl = __ffma2_rn(ph, make_float2(-1.f, -1.f), pr);   // exact
-                hi[2 * i] = __float_as_uint(ph.x); hi[2 * i + 1] = __float_as_uint(ph.y);
-                lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);
-              }
-              if (h == 0) {
-                tick(t_gen);
-                hand_over();          // the previous unit: its stores have long landed
-                tick(t_st);
-                if (!ok) tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                tick(t_aempty);
-              }
-              tmem_st8(a_tmem + h * 8, hi);
-              tmem_st8(a_tmem + 32 + h * 8, lo);
-            }
-            tick(t_gen);
+            for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + ra_off[j] + v4 * 16);
           }
-          pending = true;
-          pending_ab = ab;
-          ++n_gen;
+#pragma unroll
+          for (int half = 0; half < CH / HC; ++half) {
+            const uint32_t ab = n_gen % NABUF;
+            const uint32_t par = ((n_gen / NABUF) & 1u) ^ 1u;
+            const uint32_t a_tmem = a_tmem0 + ab * (2 * HC);
+            const uint32_t ok = mbar_test(bar_aempty + ab * 8, par);
+            if (idle[j]) {
+              hand_over();
+              if (!ok) tc_wait(bar_aempty + ab * 8, par);
+            } else {
+#pragma unroll
+              for (int hh = 0; hh < HC / 8; ++hh) {   // 8 cells at a time
+                const int h = half * (HC / 8) + hh;
+                const float4 b0 = (EXP & 4) ? own[(2 * h + 2) % 8] : lds128(cbase + rb_off[j] + h * 32), b1 = (EXP & 4) ? own[(2 * h + 3) % 8] : lds128(cbase + rb_off[j] + h * 32 + 16);
+                const float4 a0 = own[2 * h], a1 = own[2 * h + 1];
+                const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+                const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 pr = __fmul2_rn(pa[i], pb[i]);
+                  // hi = product rounded to nearest tf32 (11 bits): the low part is then sign-symmetric and
+                  // at most 2^-12 |P|, so the tensor core's truncation of it costs 2^-23 instead of 2^-22
+                  const float2 ph = (EXP & 8) ? pr : make_float2(__uint_as_float((__float_as_uint(pr.x) + 0x1000u) & 0xFFFFE000u),
+                                                __uint_as_float((__float_as_uint(pr.y) + 0x1000u) & 0xFFFFE000u));
+                  const float2 pl = (EXP & 8) ? pr : __ffma2_rn(ph, make_float2(-1.f, -1.f), pr);   // exact
+                  hi[2 * i] = __float_as_uint(ph.x); hi[2 * i + 1] = __float_as_uint(ph.y);
+                  lo[2 * i] = __float_as_uint(pl.x); lo[2 * i + 1] = __float_as_uint(pl.y);
+                }
+                if (hh == 0) {
+                  tick(t_gen);
+                  hand_over();          // the previous half unit: its stores have long landed
+                  tick(t_st);
+                  if (!ok) tc_wait(bar_aempty + ab * 8, par);
+                  tc_fence_after();
+                  tick(t_aempty);
+                }
+                if (!(EXP & 2)) {
+                  tmem_st8(a_tmem + hh * 8, hi);
+                  tmem_st8(a_tmem + HC + hh * 8, lo);
+                } else {
+                  asm volatile("" ::"r"(hi[0] ^ hi[1] ^ hi[2] ^ hi[3] ^ hi[4] ^ hi[5] ^ hi[6] ^ hi[7] ^ lo[0] ^ lo[1] ^ lo[2] ^ lo[3] ^ lo[4] ^ lo[5] ^ lo[6] ^ lo[7]));
+                }
+              }
+              tick(t_gen);
+            }
+            pending = true;
+            pending_ab = ab;
+            ++n_gen;
+            if constexpr (!DEFER) { hand_over(); tick(t_st); }   // one buffer: the MMAs must start at once
+          }
         }
       }
     }
@@ -404,130 +451,105 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
   }
 }
 
-// Drain warp (team, q): after a unit's window has had its MMAs, adds the accumulator of TMEM
-// lanes [32q, 32q+32) into fp32 registers (round to nearest) and releases the accumulator.  The
-// registers are 12 blocks of 8 columns; the block a column group goes to is warp-uniform.
-// (separate members and an if-chain: an array indexed through a switch is turned into a dynamically
-// indexed local-memory array by the compiler)
-struct DrainAcc {
-  float2 b0[4], b1[4], b2[4], b3[4], b4[4], b5[4], b6[4], b7[4], b8[4], b9[4], b10[4], b11[4];
-};
-#define BSK_TC_FOR_BLOCKS(X) X(0, b0) X(1, b1) X(2, b2) X(3, b3) X(4, b4) X(5, b5) X(6, b6) X(7, b7) X(8, b8) X(9, b9) X(10, b10) X(11, b11)
-__device__ __forceinline__ void add4(float2 (&a)[4], const float2 (&v)[4]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) a[c] = __fadd2_rn(a[c], v[c]);
-}
-__device__ __forceinline__ void add_block(DrainAcc& acc, int blk, const float2 (&v)[4]) {
-#define BSK_TC_ADD(K, M) if (blk == K) { add4(acc.M, v); return; }
-  BSK_TC_FOR_BLOCKS(BSK_TC_ADD)
-#undef BSK_TC_ADD
-}
-__device__ __forceinline__ void drain_unit(DrainAcc& acc, int blk0, int nblk, uint32_t d_tmem, uint32_t bar_full,
-                                           uint32_t bar_empty, uint32_t parity, int lane, long long& prof_wait,
-                                           long long& prof_work) {
-  long long t0 = 0;
-  if constexpr (PROF) t0 = clock64();
-  tc_wait(bar_full, parity);
-  tc_fence_after();
-  if constexpr (PROF) { const long long now = clock64(); prof_wait += now - t0; t0 = now; }
-#pragma unroll 1
-  for (int g0 = 0; g0 < nblk; ++g0) {   // one 8-column group at a time (the drain is not throughput critical)
-    float2 v0[4];
-    tmem_ld8v(d_tmem + g0 * 8, v0);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    pin8(v0);
-    add_block(acc, blk0 + g0, v0);
-  }
-  tc_fence_before();
-  nbar_arrive((int)bar_empty, 160);      // named barrier 5 + unit: the issuer may start the unit's next window
-  if constexpr (PROF) prof_work += clock64() - t0;
-}
-
-__device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint32_t tbase, int team, int q, int lane) {
-  DrainAcc acc;
-#define BSK_TC_ZERO(K, M) _Pragma("unroll") for (int c = 0; c < 4; ++c) acc.M[c] = make_float2(0.f, 0.f);
-  BSK_TC_FOR_BLOCKS(BSK_TC_ZERO)
-#undef BSK_TC_ZERO
-  // few live scalars next to the 96 accumulators (120 registers): the units' first block and block
-  // count are packed into one word (8 bits per unit), the window parities into another
-  const int my_nu = p.nu[team];
-  uint32_t cfg = 0, used = 0;
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) {
-    const uint32_t b0 = (uint32_t)p.ublk0[team * UPT + j], nb = j < my_nu ? (uint32_t)p.uncol[team * UPT + j] / 8u : 0u;
-    cfg |= (b0 | (nb << 4)) << (8 * j);
-    used = max(used, b0 + nb);
-  }
-  const uint32_t d_base = tbase + ((uint32_t)(q * 32) << 16) + TM_D + (uint32_t)team * TEAMCOLS;
-  const uint32_t bar_full = bars + (D_FULL + team * UPT) * 8;     // D_EMPTY follows NUNITS barriers later
-  uint32_t parity = 0;     // bit j: parity of unit j's next window
-  int since_flush = 0;
+// Drain warp (grp, q): for the units u with u % 2 == grp, after the unit's window has had its
+// MMAs, D2 += D1 on TMEM lanes [32q, 32q+32) (through registers, round to nearest), and the
+// first-level accumulator is released.  Every flush_chunks chunks D2 goes to the float64 partials.
+__device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint32_t tbase, int grp, int q, int lane) {
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+  const uint32_t d1 = tbase + lane_sel + TM_D1, d2 = tbase + lane_sel + TM_D2;
+  uint32_t parity = 0;     // bit u: parity of unit u's next window
   long long d_wait = 0, d_work = 0;
-  uint32_t n0 = 0;
+  const float2 zero4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  // second-level accumulators start at zero
+  for (int u = grp; u < NUNITS; u += 2)
+    for (int b = 0; b < p.uncol[u] / 8; ++b) tmem_st8f(d2 + p.udcol[u] + b * 8, zero4);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  auto drain_u = [&](int u) {
+    const int nb = p.uncol[u] / 8;
+    if (nb == 0) return;
+    long long t0 = 0;
+    if constexpr (PROF) t0 = clock64();
+    tc_wait_lazy(bars + (D_FULL + u) * 8, (parity >> u) & 1u);
+    tc_fence_after();
+    if constexpr (PROF) { const long long now = clock64(); d_wait += now - t0; t0 = now; }
+    const uint32_t c0 = p.udcol[u];
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // this thread's earlier D2 stores (long done)
+#pragma unroll 1
+    for (int b = 0; b < nb; ++b) {
+      float2 v[4], w[4];
+      tmem_ld8v(d1 + c0 + b * 8, v);
+      tmem_ld8v(d2 + c0 + b * 8, w);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      pin8(v);
+      pin8(w);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = __fadd2_rn(w[c], v[c]);
+      tmem_st8f(d2 + c0 + b * 8, w);
+    }
+    tc_fence_before();      // the loads of D1 are complete (wait::ld): the MMAs may overwrite it
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + (D_EMPTY + u) * 8);
+    parity ^= 1u << u;
+    if constexpr (PROF) d_work += clock64() - t0;
+  };
   auto flush = [&]() {
-    double* my_partial = p.partial + ((int64_t)blockIdx.x * NTEAMS + team) * ((int64_t)TEAMCOLS * 128) + q * 32 + lane;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    double* my_partial = p.partial + (int64_t)blockIdx.x * ((int64_t)DCOLS * 128) + q * 32 + lane;
     const uint64_t pol = policy_evict_last();
-#define BSK_TC_FLUSH(K, M)                                                                         \
-  if (K < used) {                                                                                  \
-    _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                \
-      red_add_f64_hint(my_partial + (int64_t)(K * 8 + 2 * c) * 128, acc.M[c].x, pol);      \
-      red_add_f64_hint(my_partial + (int64_t)(K * 8 + 2 * c + 1) * 128, acc.M[c].y, pol);  \
-      acc.M[c] = make_float2(0.f, 0.f);                                                            \
-    }                                                                                              \
-  }
-    BSK_TC_FOR_BLOCKS(BSK_TC_FLUSH)
-#undef BSK_TC_FLUSH
+    for (int u = grp; u < NUNITS; u += 2) {
+      const int nb = p.uncol[u] / 8;
+      const uint32_t c0 = p.udcol[u];
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        float2 w[4];
+        tmem_ld8v(d2 + c0 + b * 8, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        pin8(w);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          red_add_f64_hint(my_partial + (int64_t)(c0 + b * 8 + 2 * c) * 128, w[c].x, pol);
+          red_add_f64_hint(my_partial + (int64_t)(c0 + b * 8 + 2 * c + 1) * 128, w[c].y, pol);
+        }
+        tmem_st8f(d2 + c0 + b * 8, zero4);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   };
   const uint32_t gtot = (uint32_t)((p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) * NCH);
-  auto drain_j = [&](uint32_t j) {
-    const uint32_t nb = (cfg >> (8 * j + 4)) & 15u, b0 = (cfg >> (8 * j)) & 15u;
-    if (nb > 0) {
-      drain_unit(acc, (int)b0, (int)nb, d_base + b0 * 8, bar_full + j * 8, (uint32_t)(5 + team * UPT + (int)j), (parity >> j) & 1u,
-                 lane, d_wait, d_work);
-      parity ^= 1u << j;
-      if (j == 0) ++n0;
-    }
-  };
+  int since_flush = 0;
 #pragma unroll 1
   for (uint32_t g = 0; g + 1 < gtot; ++g) {
-    // the units that close their window after chunk g: (g + team * UPT + j) % WIN == WIN - 1
-    for (uint32_t j = (2 * WIN - 1 - (g + (uint32_t)team * UPT) % WIN) % WIN; j < UPT; j += WIN) drain_j(j);
+    // the units that close their window after chunk g: (g + u) % WIN == WIN - 1, u % 2 == grp
+    for (int u = (int)((2 * WIN - 1 - g % WIN) % WIN); u < NUNITS; u += WIN)
+      if ((u & 1) == grp) drain_u(u);
     if (++since_flush >= p.flush_chunks) {
       flush();
       since_flush = 0;
     }
   }
   if (gtot > 0)      // after the last chunk every unit closes
-    for (uint32_t j = 0; j < UPT; ++j) drain_j(j);
+    for (int u = grp; u < NUNITS; u += 2) drain_u(u);
   flush();
   if constexpr (PROF) {
     if (blockIdx.x == 0 && q == 0 && lane == 0 && p.prof) {
-      p.prof[(2 * NTEAMS + team) * 8 + 0] = d_wait;
-      p.prof[(2 * NTEAMS + team) * 8 + 1] = d_work;
-      p.prof[(2 * NTEAMS + team) * 8 + 2] = n0;
+      p.prof[(NTEAMS + NISSUE + grp) * 8 + 0] = d_wait;
+      p.prof[(NTEAMS + NISSUE + grp) * 8 + 1] = d_work;
     }
   }
 }
 
-// MMA issuer of one team: 12 MMAs per unit and chunk into the unit's own accumulator
-__device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase, int team) {
+// MMA issuer `iss`: for the teams iss, iss + NISSUE, ...: 6 MMAs per half unit into the unit's own
+// first-level accumulator
+__device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase, int iss) {
   const uint32_t leader = elect_one();
   const int N = p.ncols;
   const uint32_t lbo = (uint32_t)(N / 8) * 128u;     // next 4-cell group of the image
-  const int my_nu = p.nu[team];
-  uint32_t idesc[UPT], coff[UPT], dblk[UPT];
+  const uint32_t gtot = (uint32_t)((p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) * NCH);
+  uint32_t nwin = 0;                       // bit u: parity of unit u's window count
+  uint32_t n_unit[NTEAMS / NISSUE];
 #pragma unroll
-  for (int j = 0; j < UPT; ++j) {
-    dblk[j] = (uint32_t)p.ublk0[team * UPT + j];
-    idesc[j] = make_idesc_tf32(j < my_nu ? p.uncol[team * UPT + j] : 8);
-    coff[j] = (uint32_t)p.ucol0[team * UPT + j];     // first column, = 16-byte units into an image group
-  }
-  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t gtot = (uint32_t)(my_tiles * NCH);
-  uint32_t nwin[UPT];
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) nwin[j] = 0;
-  uint32_t n_unit = 0, g = 0;
+  for (int k = 0; k < NTEAMS / NISSUE; ++k) n_unit[k] = 0;
+  uint32_t g = 0;
   long long m_afull = 0, m_dempty = 0, m_issue = 0, m_bfull = 0, m_mark = 0, m_start = 0;
   if constexpr (PROF) m_start = clock64();
   int it = 0;
@@ -543,39 +565,45 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
     const uint32_t d_hi32 = (uint32_t)(make_desc(img_hi, lbo, 128u) >> 32);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c, ++g) {
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < UPT; ++j) {
-        if (j >= my_nu) continue;
-        const int u = team * UPT + j;
-        const uint32_t n = n_unit++;
-        const uint32_t ab = n & 1u;
-        if constexpr (PROF) m_mark = clock64();
-        nbar_sync(1 + team * 2 + (int)ab, 160);
-        if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
-        const bool opens = win_opens(g, u);
-        if (opens && nwin[j] > 0)    // first chunk of a window: the unit's accumulator must have been drained
-          nbar_sync(5 + u, 160);
-        tc_fence_after();
-        if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
-        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + dblk[j] * 8u;
-        const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
-        const uint32_t id = idesc[j];
-        const uint32_t o0 = coff[j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
-        const bool closes = win_closes(g, u, gtot);
-        if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < CH / 8; ++ks) {
-            const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
-            mma_tf32_ts(d, a + 32 + ks * 8, dh_lo + o, d_hi32, id, (ks == 0 && opens) ? 0u : 1u);   // P_lo * C_hi
-            mma_tf32_ts(d, a + ks * 8, dl_lo + o, d_hi32, id, 1u);                                  // P_hi * C_lo
-            mma_tf32_ts(d, a + ks * 8, dh_lo + o, d_hi32, id, 1u);                                  // P_hi * C_hi
+        for (int half = 0; half < CH / HC; ++half) {
+#pragma unroll
+          for (int k = 0; k < NTEAMS / NISSUE; ++k) {
+            const int team = iss + k * NISSUE;
+            if (j >= p.nu[team]) continue;
+            const int u = team * UPT + j;
+            const bool opens = win_opens(g, u), closes = win_closes(g, u, gtot);
+            const uint32_t n = n_unit[k]++;
+            const uint32_t ab = n % NABUF;
+            if constexpr (PROF) m_mark = clock64();
+            nbar_sync(1 + team * NABUF + (int)ab, 160);
+            if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
+            if (opens && half == 0 && !(EXP & 64))    // first hand-over of a window: the unit's accumulator must have been drained
+              tc_wait(bars + (D_EMPTY + u) * 8, ((nwin >> u) & 1u) ^ 1u);
+            tc_fence_after();
+            if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
+            const uint32_t d = tbase + TM_D1 + p.udcol[u];
+            const uint32_t a = tbase + TM_A + (uint32_t)team * (NABUF * 2 * HC) + ab * (2 * HC);
+            const uint32_t id = make_idesc_tf32(p.uncol[u]);
+            const uint32_t o0 = (uint32_t)p.ucol0[u] + (uint32_t)(c * (CH / 4) + half * (HC / 4)) * (uint32_t)N;
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < ((EXP & 1) ? 0 : HC / 8); ++ks) {
+                const uint32_t o = o0 + (uint32_t)(ks * 2) * (uint32_t)N;
+                mma_tf32_ts(d, a + HC + ks * 8, dh_lo + o, d_hi32, id, (ks == 0 && half == 0 && opens) ? 0u : 1u);   // P_lo * C_hi
+                mma_tf32_ts(d, a + ks * 8, dl_lo + o, d_hi32, id, 1u);                                               // P_hi * C_lo
+                mma_tf32_ts(d, a + ks * 8, dh_lo + o, d_hi32, id, 1u);                                               // P_hi * C_hi
+              }
+              tc_commit(bars + (A_EMPTY + team * NABUF + ab) * 8);
+              if (closes && half == CH / HC - 1 && !(EXP & 64)) tc_commit(bars + (D_FULL + u) * 8);
+            }
+            if (closes && half == CH / HC - 1) nwin ^= 1u << u;
+            __syncwarp();
+            if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
           }
-          tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
-          if (closes) tc_commit(bars + (D_FULL + u) * 8);
         }
-        if (closes) ++nwin[j];
-        __syncwarp();
-        if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
       }
     }
     if (leader) tc_commit(bars + (B_EMPTY + buf) * 8);
@@ -583,7 +611,7 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
   }
   if constexpr (PROF) {
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && p.prof) {
-      long long* o = p.prof + (NTEAMS + team) * 8;
+      long long* o = p.prof + (NTEAMS + iss) * 8;
       o[0] = m_afull; o[1] = m_dempty; o[2] = m_issue; o[3] = m_bfull; o[4] = clock64() - m_start;
     }
   }
@@ -595,18 +623,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
   const uint32_t bars = smem_u32(bar_ptr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int W_DRAIN = NTEAMS * 4, W_TMA = 2 * W_DRAIN, W_MMA0 = W_TMA + 1, W_CONV = W_MMA0 + NTEAMS;
+  constexpr int W_DRAIN = NGEN / 32, W_TMA = W_DRAIN + NDRAIN / 32, W_MMA0 = W_TMA + 1;
 
   if (tid == 0) {
     for (int b = 0; b < MAXRAWBUF; ++b) {
       mbar_init(&bar_ptr[RAW_FULL + b], 1);
-      mbar_init(&bar_ptr[RAW_EMPTY + b], NTEAMS * 4);
+      mbar_init(&bar_ptr[RAW_EMPTY + b], NGEN / 32);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_ptr[B_FULL + b], NTEAMS * 4);
-      mbar_init(&bar_ptr[B_EMPTY + b], NTEAMS);
+      mbar_init(&bar_ptr[B_FULL + b], NGEN / 32);
+      mbar_init(&bar_ptr[B_EMPTY + b], NISSUE);
     }
-    for (int b = 0; b < 2 * NTEAMS; ++b) {
+    for (int b = 0; b < NABUF * NTEAMS; ++b) {
       mbar_init(&bar_ptr[A_FULL + b], 4);
       mbar_init(&bar_ptr[A_EMPTY + b], 1);
     }
@@ -630,13 +658,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   const uint32_t tbase = *tmem_slot;
 
   if (warp < W_DRAIN) {
-    team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);     // keeps its 96 registers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
+    team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);
   } else if (warp < W_TMA) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
-    drain_loop(p, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
+    if (!(EXP & 64)) drain_loop(p, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
-    if (warp == W_TMA) {
+    if (warp == W_TMA && !(EXP & 128)) {
       // ---- TMA producer: raw [row][cell] tiles, nbuf - 1 tiles ahead of the generators
       const uint64_t pol = policy_evict_first();
       // this lane's raw rows (slots lane, lane + 32, ...): pointers of the rows that are really loaded
@@ -654,7 +683,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it % p.nbuf;
-        tc_wait(bars + (RAW_EMPTY + buf) * 8, ((uint32_t)(it / p.nbuf) & 1u) ^ 1u);
+        tc_wait_lazy(bars + (RAW_EMPTY + buf) * 8, ((uint32_t)(it / p.nbuf) & 1u) ^ 1u);
         if (lane == 0) mbar_expect_tx(&bar_ptr[RAW_FULL + buf], (uint32_t)(nload * TL * 4));
         __syncwarp();
         unsigned char* dst = const_cast<unsigned char*>(smem) + OFF_RAW + buf * p.rawb;
@@ -662,9 +691,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
         for (int k = 0; k < (MAXRAW + 31) / 32; ++k)
           if (src[k]) bulk_g2s_hint(dst + (lane + 32 * k) * RAW_STRIDE, src[k] + tile * TL, TL * 4, &bar_ptr[RAW_FULL + buf], pol);
       }
-    } else if (warp == W_CONV) {
-      // spare warp
-    } else {
+    } else if (warp < W_MMA0 + NISSUE) {
       mma_loop(p, smem, bars, tbase, warp - W_MMA0);
     }
   }

@@ -1,0 +1,492 @@
+// Host-side schedule of the tensor-core contraction (plain C++, no CUDA): which pair rows each
+// generator lane forms in each unit, which accumulator column every triangle reads, and how a
+// list that does not fit one launch is cut into passes.  See contract_tc.cuh for the kernel.
+//
+// Vocabulary.  Rows of the field table are handled in aligned groups of 8.  A triangle
+// (r1,r2,r3) -- the reference's np.sum(f[r1]*f[r2]*f[r3]), bskit/main.py:1875 -- is sorted
+// a <= b <= c: the pair (a,b) is generated on the CUDA cores, c is the accumulator column.
+// A "class" is a pair of groups (ga <= gb); one of the two groups "hosts" it: a generator warp
+// that hosts group h keeps row 8h + (lane & 7) in registers and meets the partner group through
+// shared memory.  A class is two "pieces" (warp x unit slots, 32 pair rows each, together all
+// 64 ordered pairs of the two groups).  A pass has 8 warp slots (2 teams x 4 warps) x 4 units.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <set>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+
+// BSK_TC_DEBUG=1 prints why a list was found not eligible
+#define BSK_TCS_FAIL(msg) do { if (getenv("BSK_TC_DEBUG")) fprintf(stderr, "tc schedule: not eligible: %s (line %d)\n", msg, __LINE__); return false; } while (0)
+
+namespace bsk {
+namespace tcs {
+
+#ifndef BSK_TC_UPT
+#define BSK_TC_UPT 4
+#endif
+constexpr int kTeams = 4, kUpt = BSK_TC_UPT, kUnits = kTeams * kUpt, kWarpSlots = kTeams * 4;
+constexpr int kMaxColGroups = 5;     // 40 column rows per pass
+constexpr int kMaxRawGroups = 15;    // 120 raw rows per pass
+constexpr int kPassCols = 128;       // accumulator columns per pass (== tc::DCOLS)
+constexpr int kMaxUnitCols = 40;     // N of one MMA
+constexpr int kCapTot = kPassCols;
+
+// row of the partner group met by lane l of a piece (see contract_tc.cuh)
+inline int partner_index(int lane, int piece) {
+  const int k = lane >> 1;
+  return ((k & 7) + 2 * piece + (k >> 3)) & 7;
+}
+
+struct Pass {
+  int nraw = 0;                      // raw slots (multiple of 8)
+  std::vector<int> rawrow;           // [nraw] field-table row or -1
+  int ncols = 0;                     // window columns (multiple of 8)
+  int colslot[kMaxColGroups] = {0, 0, 0, 0, 0};
+  int nu[kTeams] = {0};
+  int col0[kUnits] = {0}, ncol[kUnits] = {0};
+  int dcol[kUnits] = {0};            // first accumulator column of the unit
+  std::vector<uint32_t> lane_tab;    // [kUnits][128]: a_slot | b_slot << 8
+  int64_t mma_cost = 0;              // sum over units of max(11, ncol/2): cycles per 8 cells and MMA term
+  int pieces = 0;
+};
+
+struct Schedule {
+  std::vector<Pass> passes;
+  std::vector<int64_t> tri_slot;     // per triangle: pass * pass_stride + column * 128 + lane-in-unit
+  int64_t pass_stride = 0;           // slots per pass and CTA (kCapTot * 128)
+  double est_cycles = 0.0;           // estimated cycles per 32-cell chunk, summed over the passes
+  bool cover = false;                // pairs chosen by the class cover (else: the two smallest rows)
+};
+
+namespace detail {
+
+struct Lcg {
+  uint64_t s;
+  explicit Lcg(uint64_t seed) : s(seed * 2862933555777941757ull + 3037000493ull) {}
+  uint32_t next() {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(s >> 33);
+  }
+  int below(int n) { return (int)(next() % (uint32_t)n); }
+};
+
+struct Piece {
+  int host = -1, part = -1, piece = 0;   // groups, piece index
+  int lo = 1 << 30, hi = -1;             // window column range its needed pairs read (hi < lo: nothing)
+};
+
+// Column range (window positions) of the needed pairs one piece covers.  prange[(a,b)] is the
+// range of pair a <= b; a pair of a diagonal class may be covered by two lanes -- both count here,
+// the final assignment picks one.
+inline void piece_range(Piece& pc, const std::map<std::pair<int, int>, std::pair<int, int>>& prange) {
+  pc.lo = 1 << 30;
+  pc.hi = -1;
+  for (int l = 0; l < 32; ++l) {
+    const int a = 8 * pc.host + (l & 7), b = 8 * pc.part + partner_index(l, pc.piece);
+    auto it = prange.find({std::min(a, b), std::max(a, b)});
+    if (it == prange.end()) continue;
+    pc.lo = std::min(pc.lo, it->second.first);
+    pc.hi = std::max(pc.hi, it->second.second);
+  }
+}
+
+struct Placement {
+  int slot_host[kWarpSlots];
+  int pos[kWarpSlots][kUpt];     // piece index or -1
+};
+
+inline void unit_spans(const Placement& pl, const std::vector<Piece>& pcs, int lo[kUnits], int n[kUnits]) {
+  for (int t = 0; t < kTeams; ++t)
+    for (int j = 0; j < kUpt; ++j) {
+      int l = 1 << 30, h = -1;
+      for (int q = 0; q < 4; ++q) {
+        const int pi = pl.pos[t * 4 + q][j];
+        if (pi < 0 || pcs[pi].hi < 0) continue;
+        l = std::min(l, pcs[pi].lo);
+        h = std::max(h, pcs[pi].hi);
+      }
+      const int u = t * kUpt + j;
+      if (h < 0) {
+        bool any = false;
+        for (int q = 0; q < 4; ++q) any |= pl.pos[t * 4 + q][j] >= 0;
+        lo[u] = 0;
+        n[u] = any ? 8 : 0;     // pieces without needed pairs still occupy a unit
+      } else {
+        lo[u] = l / 8 * 8;
+        n[u] = h / 8 * 8 + 8 - lo[u];
+      }
+    }
+}
+
+// Estimated cycles per 32-cell chunk of a placement: the generator teams work through their units
+// one after the other (kGenCycles each, whatever the number of pieces in the unit), the MMA
+// issuers need 12 MMAs of max(11, N/2) cycles per unit; + a penalty when a unit is wider than one
+// MMA or the units of the pass need more accumulator columns than TMEM has for them.
+constexpr double kGenCycles = 450.0;
+inline double placement_cost(const Placement& pl, const std::vector<Piece>& pcs, bool* feasible = nullptr) {
+  int lo[kUnits], n[kUnits];
+  unit_spans(pl, pcs, lo, n);
+  double mma = 0.0, penalty = 0.0;
+  int team_units[kTeams] = {0};
+  bool ok = true;
+  int sum = 0, most = 0;
+  for (int t = 0; t < kTeams; ++t) {
+    for (int j = 0; j < kUpt; ++j) {
+      const int w = n[t * kUpt + j];
+      if (w > 0) { mma += std::max(11.0, w / 2.0); ++team_units[t]; }
+      sum += w;
+      if (w > kMaxUnitCols) { ok = false; penalty += 1000.0 + 10.0 * (w - kMaxUnitCols); }
+    }
+    most = std::max(most, team_units[t]);
+  }
+  if (sum > kPassCols) { ok = false; penalty += 1000.0 + 10.0 * (sum - kPassCols); }
+  if (feasible) *feasible = ok;
+  const double gen = kGenCycles * most;
+  return std::max(gen, 12.0 * mma) + 0.05 * (gen + 12.0 * mma) + penalty;
+}
+
+// Place the classes of one pass.  Returns false when no feasible placement was found.
+inline bool place_pass(const std::vector<std::pair<int, int>>& cls,
+                       const std::map<std::pair<int, int>, std::pair<int, int>>& prange, uint64_t seed,
+                       Placement& best, std::vector<Piece>& best_pcs, double* best_cost_out = nullptr) {
+  if ((int)cls.size() * 2 > kWarpSlots * kUpt) return false;
+  double best_cost = 1e300;
+  bool found = false;
+  Lcg rnd(seed);
+  auto slot_host = [](const Placement& pl, const std::vector<Piece>& pcs, int w) {
+    for (int j = 0; j < kUpt; ++j)
+      if (pl.pos[w][j] >= 0) return pcs[pl.pos[w][j]].host;
+    return -1;
+  };
+  for (int attempt = 0; attempt < 48 || (!found && attempt < 400); ++attempt) {
+    // orientation: which group hosts each class (diagonal classes host themselves)
+    std::vector<Piece> pcs;
+    for (size_t i = 0; i < cls.size(); ++i) {
+      const bool first = cls[i].first == cls[i].second || (rnd.next() & 1);
+      for (int piece = 0; piece < 2; ++piece) {
+        Piece pc;
+        pc.host = first ? cls[i].first : cls[i].second;
+        pc.part = first ? cls[i].second : cls[i].first;
+        pc.piece = piece;
+        piece_range(pc, prange);
+        pcs.push_back(pc);
+      }
+    }
+    // initial placement: pieces in order of their first column, each into the first free position of a
+    // slot that already hosts its group, else of an empty slot (low units first)
+    std::vector<int> order(pcs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pcs[x].lo > pcs[y].lo; });
+    Placement pl;
+    for (int w = 0; w < kWarpSlots; ++w)
+      for (int j = 0; j < kUpt; ++j) pl.pos[w][j] = -1;
+    bool ok = true;
+    for (int pi : order) {
+      int bw = -1, bj = -1, bkey = 1 << 30;
+      for (int w = 0; w < kWarpSlots; ++w) {
+        const int h = slot_host(pl, pcs, w);
+        if (h != -1 && h != pcs[pi].host) continue;
+        for (int j = 0; j < kUpt; ++j)
+          if (pl.pos[w][j] < 0) {
+            const int key = j * 64 + (h == -1 ? 32 : 0) + (int)(rnd.next() & 15);
+            if (key < bkey) { bkey = key; bw = w; bj = j; }
+            break;
+          }
+      }
+      if (bw < 0) { ok = false; break; }
+      pl.pos[bw][bj] = pi;
+    }
+    if (!ok) continue;
+    double cur = placement_cost(pl, pcs);
+    for (int it = 0; it < 3000; ++it) {
+      const int m = rnd.below(10);
+      const int w1 = rnd.below(kWarpSlots), w2 = rnd.below(kWarpSlots), j1 = rnd.below(kUpt), j2 = rnd.below(kUpt);
+      if (m < 3) {                       // permute two units of one warp slot
+        if (j1 == j2) continue;
+        std::swap(pl.pos[w1][j1], pl.pos[w1][j2]);
+        const double c = placement_cost(pl, pcs);
+        if (c <= cur) cur = c; else std::swap(pl.pos[w1][j1], pl.pos[w1][j2]);
+      } else if (m < 8) {                // exchange two positions of different slots when the hosts allow it
+        if (w1 == w2) continue;
+        const int p1 = pl.pos[w1][j1], p2 = pl.pos[w2][j2];
+        if (p1 < 0 && p2 < 0) continue;
+        std::swap(pl.pos[w1][j1], pl.pos[w2][j2]);
+        bool legal = true;
+        for (int w : {w1, w2}) {
+          int h = -1;
+          for (int j = 0; j < kUpt; ++j)
+            if (pl.pos[w][j] >= 0) {
+              if (h == -1) h = pcs[pl.pos[w][j]].host;
+              else legal &= pcs[pl.pos[w][j]].host == h;
+            }
+        }
+        const double c = legal ? placement_cost(pl, pcs) : 1e300;
+        if (c <= cur) cur = c; else std::swap(pl.pos[w1][j1], pl.pos[w2][j2]);
+      } else {                           // exchange two whole warp slots (changes the teams)
+        if (w1 == w2) continue;
+        for (int j = 0; j < kUpt; ++j) std::swap(pl.pos[w1][j], pl.pos[w2][j]);
+        const double c = placement_cost(pl, pcs);
+        if (c <= cur) cur = c;
+        else
+          for (int j = 0; j < kUpt; ++j) std::swap(pl.pos[w1][j], pl.pos[w2][j]);
+      }
+    }
+    bool feasible = false;
+    cur = placement_cost(pl, pcs, &feasible);
+    if (feasible && cur < best_cost) {
+      best_cost = cur;
+      best = pl;
+      best_pcs = pcs;
+      found = true;
+    }
+  }
+  if (!found) return false;
+  for (int w = 0; w < kWarpSlots; ++w) best.slot_host[w] = slot_host(best, best_pcs, w);
+  // the units of a team in order of decreasing width, empty unit slots last
+  int lo[kUnits], n[kUnits];
+  unit_spans(best, best_pcs, lo, n);
+  for (int t = 0; t < kTeams; ++t) {
+    int order[kUpt];
+    for (int j = 0; j < kUpt; ++j) order[j] = j;
+    std::stable_sort(order, order + kUpt, [&](int x, int y) { return n[t * kUpt + x] > n[t * kUpt + y]; });
+    Placement tmp = best;
+    for (int q = 0; q < 4; ++q)
+      for (int j = 0; j < kUpt; ++j) tmp.pos[t * 4 + q][j] = best.pos[t * 4 + q][order[j]];
+    best = tmp;
+  }
+  if (best_cost_out) *best_cost_out = best_cost;
+  return true;
+}
+
+}  // namespace detail
+
+// Build the schedule; returns false when the list is not eligible (the caller then keeps the
+// FP32-pipe kernel).
+inline bool build_schedule_mode(int ntri, const int32_t* rows, int nrows, bool cover, Schedule& out) {
+  using namespace detail;
+  if (ntri < 256 || nrows < 1 || nrows > 8 * 64) return false;
+  out.passes.clear();
+  out.est_cycles = 0.0;
+  out.cover = cover;
+  out.tri_slot.assign((size_t)ntri, -1);
+  out.pass_stride = (int64_t)kCapTot * 128;
+  // Which two rows of a triangle form the generated pair is free (the product commutes): pick a
+  // small set of classes that covers every triangle (greedy set cover -- the all-triangle list of
+  // S = 40 bins needs 9 of its 15 classes, i.e. 40 % fewer pair rows to generate), then give each
+  // triangle the covering class whose column range grows least.
+  std::vector<int> ta((size_t)ntri), tb((size_t)ntri), tc_((size_t)ntri);
+  std::vector<char> cgroup_used((size_t)(nrows + 7) / 8, 0);
+  {
+    struct Opt { int a, b, c; };
+    std::vector<Opt> opts((size_t)ntri * 3);
+    for (int t = 0; t < ntri; ++t) {
+      int r[3] = {rows[3 * t], rows[3 * t + 1], rows[3 * t + 2]};
+      std::sort(r, r + 3);
+      if (r[0] < 0 || r[2] >= nrows) return false;
+      opts[3 * t + 0] = {r[0], r[1], r[2]};
+      opts[3 * t + 1] = {r[0], r[2], r[1]};
+      opts[3 * t + 2] = {r[1], r[2], r[0]};
+    }
+    auto cls_of = [](const Opt& o) { return std::make_pair(o.a / 8, o.b / 8); };
+    std::set<std::pair<int, int>> chosen;
+    std::vector<char> covered((size_t)ntri, 0);
+    int left = cover ? ntri : 0;
+    while (left > 0) {
+      std::map<std::pair<int, int>, int> gain;
+      for (int t = 0; t < ntri; ++t) {
+        if (covered[t]) continue;
+        std::pair<int, int> seen[3];
+        int ns = 0;
+        for (int k = 0; k < 3; ++k) {
+          const auto c = cls_of(opts[3 * t + k]);
+          bool dup = false;
+          for (int i = 0; i < ns; ++i) dup |= seen[i] == c;
+          if (!dup) { seen[ns++] = c; ++gain[c]; }
+        }
+      }
+      std::pair<int, int> best{-1, -1};
+      int best_gain = -1;
+      for (auto& kv : gain)
+        if (kv.second > best_gain) { best_gain = kv.second; best = kv.first; }
+      chosen.insert(best);
+      for (int t = 0; t < ntri; ++t) {
+        if (covered[t]) continue;
+        for (int k = 0; k < 3; ++k)
+          if (cls_of(opts[3 * t + k]) == best) { covered[t] = 1; --left; break; }
+      }
+    }
+    std::map<std::pair<int, int>, std::pair<int, int>> span;   // class -> [lo, hi] of its columns (rows)
+    for (int t = 0; t < ntri; ++t) {
+      int pick = cover ? -1 : 0, pick_grow = 1 << 30;
+      for (int k = 0; k < 3 && cover; ++k) {
+        const Opt& o = opts[3 * t + k];
+        if (!chosen.count(cls_of(o))) continue;
+        auto it = span.find(cls_of(o));
+        const int grow = it == span.end() ? 8 : std::max(0, it->second.first - o.c) + std::max(0, o.c - it->second.second);
+        if (grow < pick_grow) { pick_grow = grow; pick = k; }
+      }
+      const Opt& o = opts[3 * t + pick];
+      ta[t] = o.a; tb[t] = o.b; tc_[t] = o.c;
+      auto it = span.find(cls_of(o));
+      if (it == span.end()) span[cls_of(o)] = {o.c, o.c};
+      else { it->second.first = std::min(it->second.first, o.c); it->second.second = std::max(it->second.second, o.c); }
+      cgroup_used[o.c / 8] = 1;
+    }
+  }
+  // column windows: consecutive runs of <= 5 used column groups
+  std::vector<std::vector<int>> windows;
+  for (int g = 0; g < (int)cgroup_used.size(); ++g) {
+    if (!cgroup_used[g]) continue;
+    if (windows.empty() || (int)windows.back().size() == kMaxColGroups) windows.push_back({});
+    windows.back().push_back(g);
+  }
+  for (const auto& win : windows) {
+    std::map<int, int> colpos_of_group;
+    for (size_t i = 0; i < win.size(); ++i) colpos_of_group[win[i]] = (int)i * 8;
+    // pairs (and their classes) with a triangle in this window
+    std::map<std::pair<int, int>, std::pair<int, int>> prange;     // pair -> window column range
+    std::map<std::pair<int, int>, int> class_lo;                   // class -> lowest column
+    std::vector<int> tris;
+    for (int t = 0; t < ntri; ++t) {
+      auto it = colpos_of_group.find(tc_[t] / 8);
+      if (it == colpos_of_group.end()) continue;
+      tris.push_back(t);
+      const int col = it->second + tc_[t] % 8;
+      auto key = std::make_pair(ta[t], tb[t]);
+      auto pr = prange.find(key);
+      if (pr == prange.end()) prange[key] = {col, col};
+      else { pr->second.first = std::min(pr->second.first, col); pr->second.second = std::max(pr->second.second, col); }
+      auto ck = std::make_pair(ta[t] / 8, tb[t] / 8);
+      auto cl = class_lo.find(ck);
+      if (cl == class_lo.end()) class_lo[ck] = col; else cl->second = std::min(cl->second, col);
+    }
+    // classes ordered by their lowest column (descending): neighbours share column ranges
+    std::vector<std::pair<int, int>> classes;
+    for (auto& kv : class_lo) classes.push_back(kv.first);
+    std::stable_sort(classes.begin(), classes.end(), [&](const std::pair<int, int>& x, const std::pair<int, int>& y) {
+      return class_lo[x] > class_lo[y];
+    });
+    size_t next = 0;
+    while (next < classes.size()) {
+      size_t take = std::min<size_t>(kWarpSlots * kUpt / 2, classes.size() - next);
+      Placement pl;
+      std::vector<Piece> pcs;
+      std::vector<std::pair<int, int>> cls;
+      for (;; --take) {
+        if (take == 0) BSK_TCS_FAIL("no feasible placement for a pass");
+        cls.assign(classes.begin() + next, classes.begin() + next + take);
+        // raw groups this pass touches
+        std::vector<int> groups(win.begin(), win.end());
+        for (auto& c : cls) { groups.push_back(c.first); groups.push_back(c.second); }
+        std::sort(groups.begin(), groups.end());
+        groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
+        if ((int)groups.size() > kMaxRawGroups) continue;
+        if (place_pass(cls, prange, 12345u + out.passes.size() * 977u + take, pl, pcs)) break;
+      }
+      // ---- materialise the pass
+      Pass ps;
+      std::vector<int> groups(win.begin(), win.end());
+      for (auto& c : cls) { groups.push_back(c.first); groups.push_back(c.second); }
+      std::sort(groups.begin(), groups.end());
+      groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
+      std::map<int, int> slot_of_group;
+      for (size_t i = 0; i < groups.size(); ++i) slot_of_group[groups[i]] = (int)i * 8;
+      ps.nraw = (int)groups.size() * 8;
+      ps.rawrow.assign((size_t)ps.nraw, -1);
+      for (size_t i = 0; i < groups.size(); ++i)
+        for (int k = 0; k < 8; ++k)
+          if (groups[i] * 8 + k < nrows) ps.rawrow[i * 8 + k] = groups[i] * 8 + k;
+      ps.ncols = (int)win.size() * 8;
+      for (size_t i = 0; i < win.size(); ++i) ps.colslot[i] = slot_of_group[win[i]];
+      const uint32_t idle = (uint32_t)ps.nraw | ((uint32_t)ps.nraw << 8);
+      ps.lane_tab.assign((size_t)kUnits * 128, idle);
+      // where every ordered pair of this pass lives: (unit, lane-in-unit)
+      std::map<std::pair<int, int>, std::pair<int, int>> where;
+      std::set<std::pair<int, int>> cls_set(cls.begin(), cls.end());
+      for (int w = 0; w < kWarpSlots; ++w)
+        for (int j = 0; j < kUpt; ++j) {
+          const int pi = pl.pos[w][j];
+          if (pi < 0) continue;
+          const Piece& pc = pcs[pi];
+          const int u = (w / 4) * kUpt + j, q = w % 4;
+          ps.nu[w / 4] = std::max(ps.nu[w / 4], j + 1);
+          ++ps.pieces;
+          for (int l = 0; l < 32; ++l) {
+            const int a = 8 * pc.host + (l & 7), b = 8 * pc.part + partner_index(l, pc.piece);
+            ps.lane_tab[(size_t)u * 128 + q * 32 + l] =
+                (uint32_t)(slot_of_group[pc.host] + (l & 7)) | ((uint32_t)(slot_of_group[pc.part] + b % 8) << 8);
+            auto key = std::make_pair(std::min(a, b), std::max(a, b));
+            if (!where.count(key)) where[key] = {u, q * 32 + l};
+          }
+        }
+      // unit column ranges from the triangles that really read them
+      int ulo[kUnits], uhi[kUnits];
+      for (int u = 0; u < kUnits; ++u) { ulo[u] = 1 << 30; uhi[u] = -1; }
+      std::vector<int> mine;
+      for (int t : tris) {
+        if (!cls_set.count({ta[t] / 8, tb[t] / 8})) continue;
+        auto wh = where.find({ta[t], tb[t]});
+        if (wh == where.end()) BSK_TCS_FAIL("pair without a lane");
+        const int col = colpos_of_group[tc_[t] / 8] + tc_[t] % 8;
+        ulo[wh->second.first] = std::min(ulo[wh->second.first], col);
+        uhi[wh->second.first] = std::max(uhi[wh->second.first], col);
+        mine.push_back(t);
+      }
+      for (int u = 0; u < kUnits; ++u) {
+        const bool live = (u % kUpt) < ps.nu[u / kUpt];
+        if (uhi[u] < 0) { ps.col0[u] = 0; ps.ncol[u] = live ? 8 : 0; }
+        else { ps.col0[u] = ulo[u] / 8 * 8; ps.ncol[u] = uhi[u] / 8 * 8 + 8 - ps.col0[u]; }
+        if (ps.ncol[u] > kMaxUnitCols) BSK_TCS_FAIL("unit wider than one MMA");
+        if (ps.ncol[u] > 0) ps.mma_cost += std::max(11, ps.ncol[u] / 2);
+      }
+      {
+        int c = 0;
+        for (int u = 0; u < kUnits; ++u) { ps.dcol[u] = c; c += ps.ncol[u]; }
+        if (c > kPassCols) BSK_TCS_FAIL("pass needs more accumulator columns than TMEM has");
+      }
+      const int64_t base = (int64_t)out.passes.size() * out.pass_stride;
+      for (int t : mine) {
+        const auto wh = where[{ta[t], tb[t]}];
+        const int col = colpos_of_group[tc_[t] / 8] + tc_[t] % 8;
+        if (out.tri_slot[t] >= 0) BSK_TCS_FAIL("triangle in two passes");
+        const int u = wh.first;
+        out.tri_slot[t] = base + (int64_t)(ps.dcol[u] + col - ps.col0[u]) * 128 + wh.second;
+      }
+      {
+        int tu[kTeams] = {0}, most = 0;
+        for (int u = 0; u < kUnits; ++u) tu[u / kUpt] += ps.ncol[u] > 0;
+        for (int t = 0; t < kTeams; ++t) most = std::max(most, tu[t]);
+        out.est_cycles += std::max(kGenCycles * most, 12.0 * (double)ps.mma_cost) + 200.0;
+      }
+      out.passes.push_back(std::move(ps));
+      next += take;
+    }
+  }
+  for (int t = 0; t < ntri; ++t)
+    if (out.tri_slot[t] < 0) BSK_TCS_FAIL("triangle without a slot");
+  return !out.passes.empty();
+}
+
+// Build the schedule; returns false when the list is not eligible (the caller then keeps the
+// FP32-pipe kernel).  Two ways of choosing the generated pair are tried -- the two smallest rows
+// of every triangle, and the greedy class cover -- and the one with the lower estimated time wins.
+inline bool build_schedule(int ntri, const int32_t* rows, int nrows, Schedule& out) {
+  Schedule a, b;
+  const bool oka = build_schedule_mode(ntri, rows, nrows, false, a);
+  const bool okb = build_schedule_mode(ntri, rows, nrows, true, b);
+  if (!oka && !okb) return false;
+  bool pick_b = okb && (!oka || b.est_cycles < a.est_cycles);
+  if (const char* force = getenv("BSK_TC_COVER")) {       // A/B knob: 0 = two smallest rows, 1 = class cover
+    if (force[0] == '0' && oka) pick_b = false;
+    if (force[0] == '1' && okb) pick_b = true;
+  }
+  out = pick_b ? std::move(b) : std::move(a);
+  return true;
+}
+
+}  // namespace tcs
+}  // namespace bsk
