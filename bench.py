@@ -56,6 +56,9 @@ def parse():
                     help="contraction kernel of the headline step (default: the library default)")
     ap.add_argument("--mesh", default="host", choices=["host", "device"],
                     help="device: every rank generates its own slab on the GPU (no host mesh; no e2e leg)")
+    ap.add_argument("--oracle-shells", default="",
+                    help="comma separated k-bin indices: rank 0 gathers the mesh to the host, builds these shells with "
+                         "the float64 oracle on the full grid and checks every closed triangle among them (large grids)")
     ap.add_argument("--profile", action="store_true",
                     help="only the full-grid device-resident steps (for ncu); prints stage times")
     return ap.parse_args()
@@ -359,9 +362,13 @@ def main():
         eng._mark(marks, "norm_done", e_data)
         return b, ntri_v, kmean
 
-    def timed(policy, steps, warmup, with_clocks=False, contraction=None):
+    kept = {}
+
+    def timed(policy, steps, warmup, with_clocks=False, contraction=None, keep_slab=False):
         e_data, e_norm = make(policy, contraction)
         slab = e_data.local_slab(host) if host is not None else device_slab(e_data)
+        if keep_slab:
+            kept["slab"] = slab.cpu()
         for _ in range(warmup):
             out = step(e_data, e_norm, slab)
         torch.cuda.synchronize()
@@ -411,7 +418,8 @@ def main():
         torch.cuda.empty_cache()
         return res
 
-    full = timed("full", args.steps, args.warmup, with_clocks=not args.profile, contraction=args.contraction)
+    full = timed("full", args.steps, args.warmup, with_clocks=not args.profile, contraction=args.contraction,
+                 keep_slab=bool(args.oracle_shells) and host is None)
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_only": True, "ms_per_step": full["ms_per_step"],
@@ -463,6 +471,36 @@ def main():
             e2e_s, e2e_cold_s = float(t[0].item()), float(t[1].item())
         bk.set_gridinfo_cache(old_cache)
 
+    oracle_sample = None
+    if args.oracle_shells:
+        bins = sorted(int(x) for x in args.oracle_shells.split(","))
+        if host is not None:
+            mesh_np = host.numpy() if rank == 0 else None
+        else:
+            # every rank drops its slab into shared memory on the host, rank 0 assembles the mesh
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            np.save(os.path.join(shm, f"bsk_slab_{rank}.npy"), kept["slab"].numpy())
+            if world > 1:
+                dist.barrier()
+            mesh_np = None
+            if rank == 0:
+                mesh_np = np.concatenate([np.load(os.path.join(shm, f"bsk_slab_{r}.npy")) for r in range(world)], axis=0)
+            if world > 1:
+                dist.barrier()
+            os.remove(os.path.join(shm, f"bsk_slab_{rank}.npy"))
+        if rank == 0:
+            from oracle import bskit_oracle as orc
+            tarr = np.asarray(triples)
+            sel = np.flatnonzero(np.isin(tarr, bins).all(axis=1))
+            t0 = time.perf_counter()
+            want = orc.measure_unnormalized([mesh_np], syn.BOX, edges, tarr[sel], workers=cores)
+            got = full["out"][0][sel]
+            rel = np.abs(got - want) / np.abs(want)
+            oracle_sample = {"shells": bins, "triangles": int(len(sel)), "oracle": "oracle/bskit_oracle.py, float64, full grid, "
+                             "mesh gathered from the ranks", "seconds": time.perf_counter() - t0,
+                             "rel_err": [float(x) for x in rel], "max_rel_err": float(rel.max()),
+                             "B_over_rms": [float(abs(w) / np.sqrt(np.mean(full["out"][0] ** 2))) for w in want]}
+            del mesh_np
     tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
     if world > 1:
         dist.barrier()
@@ -477,6 +515,8 @@ def main():
     checks = {"auto_vs_full_max_abs_over_rms": float(np.max(np.abs(bf - ba)) / rms),
               "N_tri_max_abs_residual_before_rounding": full["ntri_residual"],
               "checksum": checksum(bf, full["out"][1], full["out"][2])}
+    if oracle_sample is not None:
+        checks["vs_oracle_sample"] = oracle_sample
     if b_api is not None:
         checks["api_vs_engine_max_abs_over_rms"] = float(np.max(np.abs(b_api["B"] - bf)) / rms)
     if host is not None and nmesh == 512 and len(edges) == 40 and os.path.exists(FIXTURE):
