@@ -519,12 +519,13 @@ class Engine:
             self.backend.shells(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols, planes2d, out[s0:s1])
 
     # -- contraction ---------------------------------------------------------- #
-    def contract(self, fields, rows, job_off=((0, 0, 0),), marks=None):
+    def contract(self, fields, rows, job_off=((0, 0, 0),), marks=None, on_device=False):
         """Triangle sums over this rank's cells, all-reduced over ranks.
 
         fields: [nrows][ncells] tensor or a list of 1-D field tensors (nrows % 4 == 0; list
         entries may alias, which is how padding rows cost no memory);
-        rows: (T,3) row triples into `fields`.  Returns float64 numpy [njobs][T].
+        rows: (T,3) row triples into `fields`.  Returns float64 numpy [njobs][T], or with
+        `on_device` the CUDA tensor (no host synchronisation: the caller fetches it later).
         """
         if torch.is_tensor(fields):
             fields = [fields[r] for r in range(fields.shape[0])]
@@ -550,7 +551,7 @@ class Engine:
         _mark(marks, "contract_done", self)
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        return sums.cpu().numpy()
+        return sums if on_device else sums.cpu().numpy()
 
     def close(self):
         self._scratch = None
@@ -639,7 +640,7 @@ def _alloc_table(shape, engine):
     return torch.empty(shape, dtype=engine.rdtype, device=engine.device)
 
 
-def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None, symmetric=False):
+def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None, symmetric=False, defer=False):
     """Evaluate every unique bin triple of `uniq` for each job.
 
     The field table has `nseg` segments (one per source: mesh A/B/C, or unit / |k| shells) with
@@ -651,6 +652,7 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
     """
     njobs = len(job_seg_off)
     out = np.empty((njobs, len(uniq)))
+    pending = []                 # (batch, device tensor): fetched at the end, or by the caller when deferred
     nbins_all = len(np.unique(uniq))
     if engine.row_capacity() // nseg < nbins_all and engine.chunk > 1 and engine.max_rows is None:
         engine.set_chunk(1)      # trade synthesis batching for field memory before cutting the list
@@ -705,17 +707,23 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
             ofields = []
             for sidx in range(nseg):
                 ofields += [octant[sidx * nb + r] for r in range(nb)] + [octant[sidx * nb]] * (seg - nb)
-            out[:, batch] = engine.contract(ofields, rows, job_off)
+            pending.append((batch, engine.contract(ofields, rows, job_off, on_device=True)))
             _mark(marks, "contract_done", engine)
             del octant, ofields
         else:
-            out[:, batch] = engine.contract(fields, rows, job_off, marks=marks)
+            pending.append((batch, engine.contract(fields, rows, job_off, marks=marks, on_device=True)))
         del table, fields
     engine.last_batches = len(batches)
-    return out
+
+    def fetch():
+        for batch, sums in pending:
+            out[:, batch] = sums.cpu().numpy() if torch.is_tensor(sums) else np.asarray(sums)
+        return out
+
+    return fetch if defer else fetch()
 
 
-def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None):
+def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None, defer=False):
     """sum_x I_a I_b I_c / M^3 for every (a,b,c) in `triples` (indices into `edges`).
 
     cubes: 1-3 spectrum cubes (auto, <AAB>, <ABC> routing as the reference's slow
@@ -729,11 +737,14 @@ def measure_triangle_sums(engine: Engine, cubes, edges, triples, marks=None):
     def synth(sidx, run, out):
         engine.synthesize(cubes[sidx], nat.KIND_DATA, 0.0, edges[run, 0], edges[run, 1], out)
 
+    if defer:      # everything is enqueued; the returned callable synchronises and fetches the result
+        fetch = _batched_contract(engine, len(cubes), synth, [route], uniq, marks, defer=True)
+        return lambda: fetch()[0][inverse] / float(engine.grid.neval) ** 3
     sums = _batched_contract(engine, len(cubes), synth, [route], uniq, marks)[0]
     return sums[inverse] / float(engine.grid.neval) ** 3
 
 
-def measure_grid_sums(engine: Engine, edges, triples, marks=None):
+def measure_grid_sums(engine: Engine, edges, triples, marks=None, defer=False):
     """(N_tri, k_mean[T,3]) from unit-amplitude and |k|-weighted shells
     (main.py:2006-2061): N_tri = sum n_a n_b n_c / M^3, k_1 = sum kappa_a n_b n_c / M^3 / N_tri ..."""
     edges = np.asarray(edges, dtype=np.float64).reshape(-1, 2)
@@ -746,7 +757,14 @@ def measure_grid_sums(engine: Engine, edges, triples, marks=None):
             engine.synthesize(None, nat.KIND_KPOW, 1.0, edges[run, 0], edges[run, 1], out)
 
     jobs = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    if defer:
+        fetch = _batched_contract(engine, 2, synth, jobs, uniq, marks, symmetric=True, defer=True)
+        return lambda: _finish_grid_sums(engine, fetch() / float(engine.grid.neval) ** 3, inverse)
     sums = _batched_contract(engine, 2, synth, jobs, uniq, marks, symmetric=True) / float(engine.grid.neval) ** 3
+    return _finish_grid_sums(engine, sums, inverse)
+
+
+def _finish_grid_sums(engine, sums, inverse):
     ntri = np.rint(sums[0])                      # an exact triangle count (integer valued)
     resid = float(np.max(np.abs(sums[0] - ntri))) if len(ntri) else 0.0
     engine.last_ntri_residual = resid
