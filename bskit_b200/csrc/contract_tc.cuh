@@ -237,6 +237,7 @@ __device__ __forceinline__ bool win_opens(uint32_t g, int u) { return g == 0 || 
 // converter warp pair could not keep up once the generators got faster): raw fp32 -> tf32 hi
 // (round to nearest) + lo.  Thread gt owns column gt & 63 (if it exists) and the 4-cell groups
 // g = (gt >> 6) + 4k: 8 independent items per thread, 5 % of a tile's generator instructions.
+template <int UNR>
 __device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uint32_t img_hi, uint32_t img_lo, int gt,
                                               uint32_t col_slot) {
   const int l = gt & 63;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void convert_share(const Params& p, uint32_t raw, uin
     const uint32_t ngrp = (uint32_t)(p.ncols / 8) * 128u;
     const uint32_t row = raw + col_slot * RAW_STRIDE;
     const uint32_t o = (uint32_t)(l >> 3) * 128u + (uint32_t)(l & 7) * 16u;
-#pragma unroll
+#pragma unroll UNR
     for (int k = 0; k < TL / 16; ++k) {
       const uint32_t g = (uint32_t)(gt >> 6) + 4u * k;
       const float4 v = lds128(row + g * 16u);
@@ -299,8 +300,6 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
       have = true;
     }
   }
-  const int gt = team * 128 + q * 32 + lane;
-  const uint32_t col_slot = (gt & 63) < p.ncols ? (uint32_t)(p.colslot[(gt & 63) >> 3] + (gt & 7)) : 0u;
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
   const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
@@ -327,15 +326,6 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     tc_wait(bars + (RAW_FULL + buf) * 8, (uint32_t)(it / p.nbuf) & 1u);
     tick(t_raw);
     const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb) + order_token();
-    {   // this thread's share of the tile's operand images (the MMAs of tile it-2 have released them)
-      const int bbuf = it & 1;
-      tc_wait(bars + (B_EMPTY + bbuf) * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      convert_share(p, raw, smem_u32(smem + OFF_BIMG + (bbuf * 2 + 0) * BIMG_BYTES),
-                    smem_u32(smem + OFF_BIMG + (bbuf * 2 + 1) * BIMG_BYTES), gt, col_slot);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + (B_FULL + bbuf) * 8);
-      tick(t_raw);
-    }
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       const uint32_t cbase = raw + c * (CH * 4);
@@ -443,7 +433,8 @@ __device__ __forceinline__ void drain_unit(DrainAcc& acc, int blk0, int nblk, ui
   if constexpr (PROF) prof_work += clock64() - t0;
 }
 
-__device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint32_t tbase, int team, int q, int lane) {
+__device__ __forceinline__ void drain_loop(const Params& p, const unsigned char* smem, uint32_t bars, uint32_t tbase, int team,
+                                           int q, int lane) {
   DrainAcc acc;
 #define BSK_TC_ZERO(K, M) _Pragma("unroll") for (int c = 0; c < 4; ++c) acc.M[c] = make_float2(0.f, 0.f);
   BSK_TC_FOR_BLOCKS(BSK_TC_ZERO)
@@ -479,6 +470,26 @@ __device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint3
 #undef BSK_TC_FLUSH
   };
   const uint32_t gtot = (uint32_t)((p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) * NCH);
+  // The drain warps, which wait most of the time, also turn raw tile `it` into the operand images
+  // (hi = tf32 rounded to nearest, lo = rest) one tile ahead of the MMAs.  On the generator warps the
+  // same conversion stalled the A pipeline at every tile boundary (7 ms of 50,
+  // profiles/r2_tc_contract_history.md).
+  const int gt = team * 128 + q * 32 + lane;
+  const uint32_t col_slot = (gt & 63) < p.ncols ? (uint32_t)(p.colslot[(gt & 63) >> 3] + (gt & 7)) : 0u;
+  auto convert_tile = [&](uint32_t it) {
+    const uint32_t buf = it % (uint32_t)p.nbuf, bbuf = it & 1u;
+    tc_wait(bars + (RAW_FULL + buf) * 8, (it / (uint32_t)p.nbuf) & 1u);
+    tc_wait(bars + (B_EMPTY + bbuf) * 8, ((it >> 1) & 1u) ^ 1u);     // the MMAs of tile it - 2 have released the images
+    const uint32_t raw = smem_u32(smem + OFF_RAW + buf * p.rawb) + order_token();
+    convert_share<1>(p, raw, smem_u32(smem + OFF_BIMG + (bbuf * 2 + 0) * BIMG_BYTES),
+                     smem_u32(smem + OFF_BIMG + (bbuf * 2 + 1) * BIMG_BYTES), gt, col_slot);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bars + (B_FULL + bbuf) * 8);
+      mbar_arrive(bars + (RAW_EMPTY + buf) * 8);
+    }
+  };
+  if (gtot > 0) convert_tile(0);
   auto drain_j = [&](uint32_t j) {
     const uint32_t nb = (cfg >> (8 * j + 4)) & 15u, b0 = (cfg >> (8 * j)) & 15u;
     if (nb > 0) {
@@ -490,6 +501,7 @@ __device__ __forceinline__ void drain_loop(const Params& p, uint32_t bars, uint3
   };
 #pragma unroll 1
   for (uint32_t g = 0; g + 1 < gtot; ++g) {
+    if (g % NCH == 0 && g + NCH < gtot) convert_tile(g / NCH + 1);
     // the units that close their window after chunk g: (g + team * UPT + j) % WIN == WIN - 1
     for (uint32_t j = (2 * WIN - 1 - (g + (uint32_t)team * UPT) % WIN) % WIN; j < UPT; j += WIN) drain_j(j);
     if (++since_flush >= p.flush_chunks) {
@@ -515,13 +527,7 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
   const int N = p.ncols;
   const uint32_t lbo = (uint32_t)(N / 8) * 128u;     // next 4-cell group of the image
   const int my_nu = p.nu[team];
-  uint32_t idesc[UPT], coff[UPT], dblk[UPT];
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) {
-    dblk[j] = (uint32_t)p.ublk0[team * UPT + j];
-    idesc[j] = make_idesc_tf32(j < my_nu ? p.uncol[team * UPT + j] : 8);
-    coff[j] = (uint32_t)p.ucol0[team * UPT + j];     // first column, = 16-byte units into an image group
-  }
+  // (per-unit constants are read from the parameter bank where they are used: the issuer runs on 48 registers)
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t gtot = (uint32_t)(my_tiles * NCH);
   uint32_t nwin[UPT];
@@ -557,10 +563,11 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
           nbar_sync(5 + u, 160);
         tc_fence_after();
         if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
-        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + dblk[j] * 8u;
+        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + (uint32_t)p.ublk0[team * UPT + j] * 8u;
         const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
-        const uint32_t id = idesc[j];
-        const uint32_t o0 = coff[j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
+        const uint32_t id = make_idesc_tf32(p.uncol[team * UPT + j]);
+        // first column of the unit (= 16-byte units into an image group) + the chunk's 4-cell groups
+        const uint32_t o0 = (uint32_t)p.ucol0[team * UPT + j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
         const bool closes = win_closes(g, u, gtot);
         if (leader) {
 #pragma unroll
@@ -600,7 +607,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
   if (tid == 0) {
     for (int b = 0; b < MAXRAWBUF; ++b) {
       mbar_init(&bar_ptr[RAW_FULL + b], 1);
-      mbar_init(&bar_ptr[RAW_EMPTY + b], NTEAMS * 4);
+      mbar_init(&bar_ptr[RAW_EMPTY + b], 2 * NTEAMS * 4);     // generator warps (pair products) + drain warps (images)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_ptr[B_FULL + b], NTEAMS * 4);
@@ -633,7 +640,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_contract_kernel(const __grid_c
     team_loop(p, smem, bars, tbase, warp >> 2, warp & 3, lane);     // keeps its 96 registers
   } else if (warp < W_TMA) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
-    drain_loop(p, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
+    drain_loop(p, smem, bars, tbase, (warp - W_DRAIN) >> 2, warp & 3, lane);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     if (warp == W_TMA) {
