@@ -403,11 +403,17 @@ class Engine:
         """This rank's x-planes of `mesh` as a CUDA tensor.  `mesh` is the full
         (N,N,N) array (numpy / torch, any device) or already the local slab."""
         n, f = self.grid.nmesh, self.info
+        if not isinstance(mesh, np.ndarray) and not torch.is_tensor(mesh) and hasattr(mesh, "shape"):
+            # file-backed sources (bigfile.BigFileMesh over several physical files): x-slicing reads
+            # only the planes this rank owns
+            if tuple(mesh.shape) == (n, n, n):
+                mesh = mesh[f.nx0:f.nx0 + f.nxl]
+            mesh = np.asarray(mesh)
         if isinstance(mesh, np.ndarray):
             if tuple(mesh.shape) == (n, n, n):
                 mesh = mesh[f.nx0:f.nx0 + f.nxl]          # slice first: memory-mapped files stay lazy
-            if mesh.dtype not in (np.float32, np.float64):
-                mesh = mesh.astype(np.float64)
+            if mesh.dtype not in (np.float32, np.float64) or not mesh.dtype.isnative:
+                mesh = mesh.astype(np.float32 if mesh.dtype.itemsize == 4 and mesh.dtype.kind == "f" else np.float64)
             if not mesh.flags.writeable:                  # e.g. np.load(mmap_mode='r')
                 mesh = np.array(mesh)
             t = torch.from_numpy(mesh)

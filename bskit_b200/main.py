@@ -38,6 +38,7 @@ from .bins import (generate_bin_edge_list, geometric_k_mean,
                    generate_squeezed_triangle_bin_list,
                    generate_isosceles_triangle_bin_list, generate_triangle_bin_list)
 from .mesh import ArrayMesh, CompensateCIC, cast_source
+from .bigfile import BigFileMesh, save_mesh
 
 __all__ = [
     "FFTBispectrum", "ArrayMesh", "CompensateCIC",
@@ -48,7 +49,7 @@ __all__ = [
     "compute_bk_FFT_value", "bk_FFT_full", "bk_FFT_grid_info", "bk_FFT_unnormalized_value",
     "combine_gridinfo_and_unnormalized", "clear_cache", "set_gridinfo_cache",
     "subbox_multiindex_to_index", "subbox_index_to_multiindex", "field_subbox_pm", "measure_subboxes",
-    "downsample_mesh", "paint_cic",
+    "downsample_mesh", "paint_cic", "BigFileMesh", "save_mesh",
 ]
 
 F32, F64 = 0, 1

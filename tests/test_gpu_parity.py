@@ -753,3 +753,23 @@ def test_ntri_is_integer_before_rounding(bk, syn):
     assert e.last_ntri_residual < 0.05, e.last_ntri_residual
     assert ntri.max() > 1e6 and np.all(ntri == np.rint(ntri))
     e.close()
+
+
+# --- meshes in bigfile format (nbodykit BigFileMesh, measure_bs_slow.py:226) ------ #
+def test_bigfile_mesh_source(bk, syn, tmp_path):
+    n, nb = 32, 6
+    kmin, kmax, dk = syn.bench_bins(nb)
+    mesh = syn.lognormal_mesh(n, seed=4)
+    path = bk.save_mesh(str(tmp_path / "delta.bigfile"), mesh, syn.BOX, nfile=3)
+    src = bk.BigFileMesh(path, "Field", verify=True)
+    fb = bk.FFTBispectrum(src, kmin=kmin, kmax=kmax, dk=dk, grid="full")
+    assert np.array_equal(fb.attrs["BoxSize"], [syn.BOX] * 3) and int(fb.attrs["Nmesh"][0]) == n
+    got = fb.measure_bispectrum_faster(0, 10 ** 6)["B"]
+    fa = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, grid="full")
+    want = fa.measure_bispectrum_faster(0, 10 ** 6)["B"]
+    assert np.array_equal(got, want)            # same numbers through the file as through memory
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    assert_b_close(got, orc.measure_unnormalized([mesh], syn.BOX, edges, idx))
+    fb.close()
+    fa.close()
