@@ -82,3 +82,19 @@ def test_oracle_cic_painting_properties():
     rng = np.random.default_rng(0)
     pos = rng.uniform(0, box, size=(1000, 3))
     assert np.isclose(orc.paint_cic(pos, n, box).sum(), 1000.0)
+
+
+def test_tiled_mesh_identity_behind_the_c5_check():
+    """scripts/make_golden_c5.py: a mesh that repeats a small field t times per axis has
+    B_big = t^6 B_small for the same physical bins (here t = 2, 16^3 -> 32^3, aliased bins included)."""
+    from bskit_b200 import synthetic as syn
+    t, ns, nb = 2, 16, 6
+    box = 200.0
+    small = syn.gaussian_mesh(ns, seed=3, box=box).astype(np.float64)
+    big = np.tile(small, (t, t, t))
+    kmin, kmax, dk = syn.bench_bins(nb, box=box)
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_all(edges, 1)
+    b_small = orc.measure_unnormalized([small], box, edges, idx)
+    b_big = orc.measure_unnormalized([big], box * t, edges, idx)
+    assert np.allclose(b_big, b_small * float(t) ** 6, rtol=1e-9, atol=1e-9 * np.abs(b_small).max() * t ** 6)
