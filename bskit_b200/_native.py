@@ -19,7 +19,7 @@ MAX_CHUNK = 64
 #: every symbol include/bskit_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
-    "bsk_set_compensation", "bsk_plan_set_stream", "bsk_fold_even", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin",
+    "bsk_set_compensation", "bsk_plan_set_stream", "bsk_fold_even", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin", "bsk_shells_x", "bsk_shells_yz",
     "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_cplan_set_path",
     "bsk_cplan_path", "bsk_tc_schedule_info", "bsk_contract",
     "bsk_reduce_list", "bsk_paint_cic", "bsk_launch_count",
@@ -28,7 +28,7 @@ EXPORTS = (
 
 class Geometry(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "fft_precision", "no_prune", "reserved")]
+                ("nmesh", "neval", "ncrop", "precision", "world", "rank", "max_shells", "fft_precision", "no_prune", "transposed")]
 
 
 class Info(C.Structure):
@@ -36,7 +36,7 @@ class Info(C.Structure):
                 ("kx", "ky", "kz", "nx0", "nxl", "mx0", "mxl", "fwd_batch", "fwd_work_complex",
                  "planes_local_complex", "planes_all_complex", "cube_complex",
                  "xcols_complex_per_shell", "planes2d_complex_per_shell", "field_real_per_shell",
-                 "fft_work_bytes")]
+                 "fft_work_bytes", "kyl", "ky0", "xplanes_complex_per_shell", "pruned")]
 
 
 class NativeError(RuntimeError):
@@ -71,6 +71,8 @@ def lib():
     L.bsk_modes_per_bin.argtypes = [vp, ip, dp, dp, C.POINTER(C.c_int64)]
     L.bsk_shells_prepare.argtypes = [vp, ip]
     L.bsk_shells.argtypes = [vp, vp, ip, C.c_double, ip, dp, dp, vp, vp, vp]
+    L.bsk_shells_x.argtypes = [vp, vp, ip, C.c_double, ip, dp, dp, vp]
+    L.bsk_shells_yz.argtypes = [vp, ip, vp, vp, vp]
     L.bsk_cplan_create.argtypes = [C.POINTER(vp), ip, C.POINTER(C.c_int32), ip, ip]
     L.bsk_cplan_destroy.argtypes = [vp]
     L.bsk_cplan_info.argtypes = [vp, C.POINTER(C.c_int64)]

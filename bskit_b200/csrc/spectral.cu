@@ -267,7 +267,7 @@ static int get_invx(bsk_plan* p, int nsh, cufftHandle* out) {
     return BSK_OK;
   }
   int M = p->g.neval;
-  long long cols = (long long)nsh * p->info.ky * p->info.kz;
+  long long cols = (long long)nsh * p->info.kyl * p->info.kz;
   long long n[1] = {M};
   long long emb[1] = {M};
   cufftHandle h;
@@ -339,9 +339,11 @@ __global__ void narrow_rows_kernel(const double* __restrict__ src, float* __rest
   }
 }
 
-template <typename TF, typename TS>  // transform precision, storage precision
-static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int nsh,
-                       const BinEdges& be, void* xcols, void* planes2d, void* fields) {
+// Shell synthesis, first half: k-shell filter of the (local ky block of the) cube and the inverse x
+// transform of every kept column.  xcols: [M][nsh][kyl][kz], or [M][nsh][kz][kyl] on the pruned path.
+template <typename TF>
+static int shells_x_impl(bsk_plan* p, const void* cube, int kind, double kpow, int nsh,
+                         const BinEdges& be, void* xcols) {
   using C = typename Cx<TF>::type;
   const bsk_info& f = p->info;
   const int N = p->g.nmesh, M = p->g.neval;
@@ -349,28 +351,40 @@ static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int
   if (f.kx != M)  // rows of the padded x axis that no kept mode maps to must be zero
     BSK_CUDA(cudaMemsetAsync(xcols, 0, sizeof(C) * (size_t)xc, p->stream));
   shell_filter_kernel<TF><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-      (const double2*)cube, (C*)xcols, (int)f.kx, (int)f.ky, (int)f.kz, N, M, nsh, kind, kpow,
-      p->use_zpass ? 1 : 0, be, p->d_kx, p->d_ky, p->d_kz);
+      (const double2*)cube, (C*)xcols, (int)f.kx, (int)f.kyl, (int)f.kz, N, M, nsh, kind, kpow,
+      p->use_zpass ? 1 : 0, be, p->d_kx, p->d_ky + f.ky0, p->d_kz);
   count_launch();
   BSK_CUDA(cudaGetLastError());
-  cufftHandle hx, h2;
+  cufftHandle hx;
   int rc;
   if ((rc = get_invx(p, nsh, &hx))) return rc;
   if (sizeof(TF) == 4)
     BSK_FFT(cufftExecC2C(hx, (cufftComplex*)xcols, (cufftComplex*)xcols, CUFFT_INVERSE));
   else
     BSK_FFT(cufftExecZ2Z(hx, (cufftDoubleComplex*)xcols, (cufftDoubleComplex*)xcols, CUFFT_INVERSE));
+  return BSK_OK;
+}
+
+// Second half: the (y,z) transforms of this rank's x-planes.  xplanes: the x-transformed columns of the
+// planes [mx0, mx0+mxl) with the FULL ky range, [mxl][nsh][ky][kz] ([mxl][nsh][kz][ky] pruned).
+template <typename TF, typename TS>  // transform precision, storage precision
+static int shells_yz_impl(bsk_plan* p, int nsh, const void* xplanes, void* planes2d, void* fields) {
+  using C = typename Cx<TF>::type;
+  const bsk_info& f = p->info;
+  const int M = p->g.neval;
+  cufftHandle h2;
+  int rc;
   if (p->use_zpass) {  // pruned y pass (cuFFT on the kept kz columns) + fused z pass
     cufftHandle hy;
     if ((rc = get_invy(p, nsh, &hy))) return rc;
-    return zpass_run(M, sizeof(TS) == 4, xcols, planes2d, fields, (int)f.ky, (int)f.kz, nsh,
-                     (int)f.mx0, (int)f.mxl, p->d_wtab, hy, p->stream);
+    return zpass_run(M, sizeof(TS) == 4, xplanes, planes2d, fields, (int)f.ky, (int)f.kz, nsh,
+                     0, (int)f.mxl, p->d_wtab, hy, p->stream);
   }
   if ((rc = get_inv2d(p, nsh, &h2))) return rc;
   const int64_t rows = (int64_t)nsh * f.mxl * M;
   int grid = (int)(rows < 148 * 32 ? rows : 148 * 32);
-  scatter_planes_kernel<TF><<<grid, 128, 0, p->stream>>>((const C*)xcols, (C*)planes2d, M, (int)f.ky,
-                                                         (int)f.kz, nsh, (int)f.mx0, (int)f.mxl);
+  scatter_planes_kernel<TF><<<grid, 128, 0, p->stream>>>((const C*)xplanes, (C*)planes2d, M, (int)f.ky,
+                                                         (int)f.kz, nsh, 0, (int)f.mxl);
   count_launch();
   BSK_CUDA(cudaGetLastError());
   if (sizeof(TF) == sizeof(TS)) {
@@ -388,6 +402,23 @@ static int shells_impl(bsk_plan* p, const void* cube, int kind, double kpow, int
   return BSK_OK;
 }
 
+static int shells_x_dispatch(bsk_plan* p, const void* cube, int kind, double kpow, int nsh, const double* lo,
+                             const double* hi, void* xcols) {
+  BinEdges be;
+  for (int s = 0; s < nsh; ++s) {
+    be.lo[s] = lo[s];
+    be.hi[s] = hi[s];
+  }
+  for (int s = nsh; s < kMaxChunk; ++s) be.lo[s] = be.hi[s] = 0.0;
+  return p->g.fft_precision == BSK_F64 ? shells_x_impl<double>(p, cube, kind, kpow, nsh, be, xcols)
+                                       : shells_x_impl<float>(p, cube, kind, kpow, nsh, be, xcols);
+}
+
+static int shells_yz_dispatch(bsk_plan* p, int nsh, const void* xplanes, void* planes2d, void* fields) {
+  if (p->g.precision == BSK_F64) return shells_yz_impl<double, double>(p, nsh, xplanes, planes2d, fields);
+  return p->g.fft_precision == BSK_F64 ? shells_yz_impl<double, float>(p, nsh, xplanes, planes2d, fields)
+                                       : shells_yz_impl<float, float>(p, nsh, xplanes, planes2d, fields);
+}
 
 // ---------------------------------------------------------------------------
 // C ABI
@@ -425,6 +456,9 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   const bool full = (2 * g.ncrop + 1 >= N);
   BSK_REQUIRE(full ? (M == N) : (M >= 2 * g.ncrop + 2),
               "neval=%d incompatible with ncrop=%d at nmesh=%d", M, g.ncrop, N);
+  BSK_REQUIRE(g.transposed == 0 || g.transposed == 1, "transposed must be 0 or 1");
+  BSK_REQUIRE(!g.transposed || full,
+              "a transposed (y-slab) spectrum is for uncropped spectra only (2*ncrop+1 >= nmesh)");
 
   bsk_plan* p = new bsk_plan();
   p->g = g;
@@ -443,14 +477,20 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
   for (int64_t b = 1; b <= f.nxl; ++b)
     if (f.nxl % b == 0 && b * (int64_t)N * (N / 2 + 1) * 16 <= (1ll << 30)) f.fwd_batch = b;
   f.fwd_work_complex = f.fwd_batch * (int64_t)N * (N / 2 + 1);
+  // transposed: the spectrum cube (and the x-transformed columns of the shells) hold this rank's
+  // ky block only; the exchanges around them are all-to-all transposes (x-slabs <-> y-slabs)
+  f.kyl = g.transposed ? f.ky / g.world : f.ky;
+  f.ky0 = g.transposed ? f.kyl * g.rank : 0;
   f.planes_local_complex = f.nxl * f.ky * f.kz;
-  f.planes_all_complex = (int64_t)N * f.ky * f.kz;
-  f.cube_complex = f.kx * f.ky * f.kz;
-  f.xcols_complex_per_shell = (int64_t)M * f.ky * f.kz;
+  f.planes_all_complex = (int64_t)N * f.kyl * f.kz;
+  f.cube_complex = f.kx * f.kyl * f.kz;
+  f.xcols_complex_per_shell = (int64_t)M * f.kyl * f.kz;
+  f.xplanes_complex_per_shell = g.transposed ? f.mxl * f.ky * f.kz : 0;
   p->use_zpass = (g.fft_precision == BSK_F64) && zpass_supported(M) && !g.no_prune;
   f.planes2d_complex_per_shell =
       p->use_zpass ? f.mxl * (int64_t)M * f.kz : f.mxl * (int64_t)M * (M / 2 + 1);
   f.field_real_per_shell = f.mxl * (int64_t)M * M;
+  f.pruned = p->use_zpass ? 1 : 0;
 
   int rc;
   if ((rc = upload(&p->d_kx, kx_tab, f.kx, p->stream))) return rc;
@@ -471,7 +511,7 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
     if (rc) return rc;
   }
   {  // forward: strided 1-D complex transform along x on the kept (y,z) columns
-    long long cols = f.ky * f.kz;
+    long long cols = f.kyl * f.kz;
     long long n[1] = {N};
     long long emb[1] = {N};
     rc = make_plan_many(&p->fwdx, 1, n, emb, cols, 1, emb, cols, 1, CUFFT_Z2Z, cols, p->stream,
@@ -610,7 +650,7 @@ int bsk_forward_finish(bsk_plan* p, void* planes_all, void* cube) {
   BSK_REQUIRE(p && planes_all && cube, "bsk_forward_finish: null argument");
   const bsk_info& f = p->info;
   const int N = p->g.nmesh;
-  const int64_t plane = f.ky * f.kz;
+  const int64_t plane = f.kyl * f.kz;
   BSK_FFT(cufftExecZ2Z(p->fwdx, (cufftDoubleComplex*)planes_all, (cufftDoubleComplex*)planes_all,
                        CUFFT_FORWARD));
   crop_x_kernel<double><<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
@@ -633,7 +673,7 @@ int bsk_modes_per_bin(bsk_plan* p, int nbins, const double* lo, const double* hi
   BSK_CUDA(cudaMemcpyAsync(d_hi, hi, sizeof(double) * nbins, cudaMemcpyHostToDevice, p->stream));
   BSK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nbins, p->stream));
   mode_count_kernel<<<grid_for(f.cube_complex, 256), 256, 0, p->stream>>>(
-      (int)f.kx, (int)f.ky, (int)f.kz, p->g.nmesh, nbins, d_lo, d_hi, p->d_kx, p->d_ky, p->d_kz,
+      (int)f.kx, (int)f.kyl, (int)f.kz, p->g.nmesh, nbins, d_lo, d_hi, p->d_kx, p->d_ky + f.ky0, p->d_kz,
       d_cnt);
   count_launch();
   BSK_CUDA(cudaGetLastError());
@@ -657,25 +697,38 @@ int bsk_shells_prepare(bsk_plan* p, int nsh) {
   return get_inv2d(p, nsh, &h);
 }
 
+static int shells_check(bsk_plan* p, const void* cube, int kind, int nsh, const char* who) {
+  BSK_REQUIRE(nsh >= 1 && nsh <= p->g.max_shells, "%s: nsh=%d outside [1,%d]", who, nsh, p->g.max_shells);
+  BSK_REQUIRE(kind == BSK_KIND_DATA || kind == BSK_KIND_UNIT || kind == BSK_KIND_KPOW, "%s: bad kind %d", who, kind);
+  BSK_REQUIRE(kind != BSK_KIND_DATA || cube, "%s: data kind needs the spectrum cube", who);
+  return BSK_OK;
+}
+
 int bsk_shells(bsk_plan* p, const void* cube, int kind, double kpow, int nsh, const double* lo,
                const double* hi, void* xcols, void* planes2d, void* fields) {
   BSK_REQUIRE(p && lo && hi && xcols && planes2d && fields, "bsk_shells: null argument");
-  BSK_REQUIRE(nsh >= 1 && nsh <= p->g.max_shells, "bsk_shells: nsh=%d outside [1,%d]", nsh,
-              p->g.max_shells);
-  BSK_REQUIRE(kind == BSK_KIND_DATA || kind == BSK_KIND_UNIT || kind == BSK_KIND_KPOW,
-              "bsk_shells: bad kind %d", kind);
-  BSK_REQUIRE(kind != BSK_KIND_DATA || cube, "bsk_shells: data kind needs the spectrum cube");
-  BinEdges be;
-  for (int s = 0; s < nsh; ++s) {
-    be.lo[s] = lo[s];
-    be.hi[s] = hi[s];
-  }
-  for (int s = nsh; s < kMaxChunk; ++s) be.lo[s] = be.hi[s] = 0.0;
-  if (p->g.precision == BSK_F64)
-    return shells_impl<double, double>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields);
-  return p->g.fft_precision == BSK_F64
-             ? shells_impl<double, float>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields)
-             : shells_impl<float, float>(p, cube, kind, kpow, nsh, be, xcols, planes2d, fields);
+  BSK_REQUIRE(!p->g.transposed, "bsk_shells: a transposed plan needs bsk_shells_x, the host's all-to-all, bsk_shells_yz");
+  int rc;
+  if ((rc = shells_check(p, cube, kind, nsh, "bsk_shells"))) return rc;
+  if ((rc = shells_x_dispatch(p, cube, kind, kpow, nsh, lo, hi, xcols))) return rc;
+  // this rank's planes of the x-transformed columns
+  const size_t csize = p->g.fft_precision == BSK_F64 ? 16 : 8;
+  const char* xplanes = (const char*)xcols + csize * (size_t)p->info.mx0 * nsh * p->info.ky * p->info.kz;
+  return shells_yz_dispatch(p, nsh, xplanes, planes2d, fields);
+}
+
+int bsk_shells_x(bsk_plan* p, const void* cube, int kind, double kpow, int nsh, const double* lo,
+                 const double* hi, void* xcols) {
+  BSK_REQUIRE(p && lo && hi && xcols, "bsk_shells_x: null argument");
+  int rc;
+  if ((rc = shells_check(p, cube, kind, nsh, "bsk_shells_x"))) return rc;
+  return shells_x_dispatch(p, cube, kind, kpow, nsh, lo, hi, xcols);
+}
+
+int bsk_shells_yz(bsk_plan* p, int nsh, const void* xplanes, void* planes2d, void* fields) {
+  BSK_REQUIRE(p && xplanes && planes2d && fields, "bsk_shells_yz: null argument");
+  BSK_REQUIRE(nsh >= 1 && nsh <= p->g.max_shells, "bsk_shells_yz: nsh=%d outside [1,%d]", nsh, p->g.max_shells);
+  return shells_yz_dispatch(p, nsh, xplanes, planes2d, fields);
 }
 
 }  // extern "C"

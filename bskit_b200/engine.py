@@ -159,9 +159,11 @@ class NativeBackend:
     name = "cuda-sm100a"
 
     def __init__(self, grid: GridChoice, boxsize, precision, world, rank, device, max_shells,
-                 fft_precision=None, accum_precision=None, no_prune=False, contraction=None):
+                 fft_precision=None, accum_precision=None, no_prune=False, contraction=None, transposed=False):
         if device.type != "cuda":
             raise nat.NativeError("bskit_b200 runs on CUDA devices only (no CPU fallback)")
+        self.transposed = bool(transposed)
+        self.world, self.group = world, None        # the engine sets `group` (collective mode counts)
         self.lib = nat.lib()
         self.grid, self.precision, self.device = grid, precision, device
         self.fft_precision = nat.F64 if fft_precision is None else max(fft_precision, precision)
@@ -171,7 +173,7 @@ class NativeBackend:
         kx, ky, kz, _ = axis_tables(grid, boxsize)
         self._tables = (kx, ky, kz)
         geom = nat.Geometry(grid.nmesh, grid.neval, grid.ncrop, precision, world, rank, max_shells,
-                            self.fft_precision, int(bool(no_prune)), 0)
+                            self.fft_precision, int(bool(no_prune)), int(self.transposed))
         self.stream = torch.cuda.current_stream(device).cuda_stream
         handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -244,7 +246,7 @@ class NativeBackend:
     def forward_finish(self, planes_all):
         self._use_current_stream()
         f = self.info
-        cube = torch.empty((f.kx, f.ky, f.kz), dtype=torch.complex128, device=self.device)
+        cube = torch.empty((f.kx, f.kyl, f.kz), dtype=torch.complex128, device=self.device)
         nat.check(self.lib.bsk_forward_finish(self.handle, planes_all.data_ptr(), cube.data_ptr()),
                   "bsk_forward_finish")
         return cube
@@ -257,6 +259,10 @@ class NativeBackend:
         nat.check(self.lib.bsk_modes_per_bin(self.handle, len(lo), nat.dptr(lo), nat.dptr(hi),
                                              out.ctypes.data_as(C.POINTER(C.c_int64))),
                   "bsk_modes_per_bin")
+        if self.transposed and self.world > 1:       # every rank counted its ky block of the cube
+            t = torch.from_numpy(out).to(self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            out = t.cpu().numpy()
         return out
 
     def prepare_shells(self, nsh):
@@ -272,6 +278,21 @@ class NativeBackend:
                                       kind, float(kpow), len(lo), nat.dptr(lo), nat.dptr(hi),
                                       xcols.data_ptr(), planes2d.data_ptr(), fields_out.data_ptr()),
                   "bsk_shells")
+
+    def shells_x(self, cube, kind, kpow, lo, hi, xcols):
+        """First half of `shells` (transposed plans): filter of this rank's ky block + inverse x transform."""
+        self._use_current_stream()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        nat.check(self.lib.bsk_shells_x(self.handle, cube.data_ptr() if cube is not None else None,
+                                        kind, float(kpow), len(lo), nat.dptr(lo), nat.dptr(hi),
+                                        xcols.data_ptr()), "bsk_shells_x")
+
+    def shells_yz(self, nsh, xplanes, planes2d, fields_out):
+        """Second half: (y,z) transforms of this rank's x-planes (all ky) into the fields."""
+        self._use_current_stream()
+        nat.check(self.lib.bsk_shells_yz(self.handle, int(nsh), xplanes.data_ptr(), planes2d.data_ptr(),
+                                         fields_out.data_ptr()), "bsk_shells_yz")
 
     def contract(self, fields, rows, ncells, job_off):
         """fields: list of 1-D field tensors (len % 4 == 0; entries may alias); rows: (T,3)
@@ -388,10 +409,26 @@ class Engine:
         # keep each cuFFT batch below 2^31 elements and the scratch within budget
         by_elems = (2 ** 31 - 1) // max(mxl * m * m, 1)
         self.chunk = int(max(1, min(nat.MAX_CHUNK, scratch_bytes // max(per_shell, 1), by_elems)))
+        # Exchange of the distributed transforms.  A spectrum that can be cropped is all-gathered (a few
+        # MB) and every rank keeps the whole cropped cube.  When the bins reach Nyquist nothing can be
+        # cropped: the cube is then distributed in ky blocks and the exchanges are the all-to-all
+        # transposes of a slab-decomposed FFT (what pfft does under the reference, main.py:1612).
+        # BSKIT_B200_EXCHANGE=allgather|alltoall overrides (A/B timing, single-GPU tests of the split path).
+        mode = os.environ.get("BSKIT_B200_EXCHANGE", "")
+        if mode not in ("", "allgather", "alltoall"):
+            raise ValueError("BSKIT_B200_EXCHANGE must be 'allgather' or 'alltoall'")
+        self.transposed = bool(grid.full and (mode == "alltoall" or (self.world > 1 and mode != "allgather")))
+        if self.transposed:
+            kzn_t, kyl_t = grid.nmesh // 2 + 1, grid.nmesh // self.world
+            per_shell = (m * kyl_t * kzn_t + mxl * m * (kzn_t if pruned else m // 2 + 1)) * 2 * fft_itemsize
+            self.chunk = int(max(1, min(nat.MAX_CHUNK, scratch_bytes // max(per_shell, 1), by_elems)))
+        extra = {} if contraction is None else {"contraction": contraction}
+        if self.transposed:
+            extra["transposed"] = True
         self.backend = backend_cls(grid, self.boxsize, precision, self.world, self.rank,
                                    self.device, self.chunk, fft_precision=fft_precision,
-                                   accum_precision=accum_precision, no_prune=no_prune,
-                                   **({} if contraction is None else {"contraction": contraction}))
+                                   accum_precision=accum_precision, no_prune=no_prune, **extra)
+        self.backend.group = self.group
         self.info = self.backend.info
         self.ncells = int(self.info.field_real_per_shell)
         self.rdtype = torch.float32 if precision == nat.F32 else torch.float64
@@ -461,7 +498,18 @@ class Engine:
         if ready is not None:
             slab.record_stream(torch.cuda.current_stream(self.device))
         planes = self.backend.forward_local(slab)
-        if self.world > 1:
+        if self.transposed:
+            # x-slabs -> y-slabs: ky block r of every plane goes to rank r; the received blocks, in
+            # rank order, are the planes [N][kyl][kz] of this rank's ky block
+            f = self.info
+            if self.world > 1:
+                send = planes.view(f.nxl, self.world, f.kyl, f.kz).permute(1, 0, 2, 3).contiguous()
+                allp = torch.empty_like(send)
+                all_to_all_blocks(torch.view_as_real(allp), torch.view_as_real(send), self.group)
+                allp = allp.view(self.grid.nmesh, f.kyl, f.kz)
+            else:
+                allp = planes
+        elif self.world > 1:
             n = self.grid.nmesh
             allp = torch.empty((n,) + tuple(planes.shape[1:]), dtype=planes.dtype, device=planes.device)
             all_gather_concat(torch.view_as_real(allp), torch.view_as_real(planes), self.group)
@@ -522,7 +570,26 @@ class Engine:
         for s0 in range(0, nb, self.chunk):
             s1 = min(nb, s0 + self.chunk)
             xcols, planes2d = self._get_scratch(s1 - s0)
-            self.backend.shells(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols, planes2d, out[s0:s1])
+            if not self.transposed:
+                self.backend.shells(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols, planes2d, out[s0:s1])
+                continue
+            nsh, f = s1 - s0, self.info
+            self.backend.shells_x(cube, kind, kpow, lo[s0:s1], hi[s0:s1], xcols)
+            if self.world > 1:
+                # y-slabs -> x-slabs: x chunk r of the transformed columns goes to rank r (staged in the
+                # planes2d scratch, which the (y,z) passes only write later), then the ky blocks of
+                # the senders are interleaved back into the full ky axis, in place of xcols
+                nx = nsh * f.xcols_complex_per_shell
+                send, stage = xcols[:nx], planes2d[:nx]
+                all_to_all_blocks(torch.view_as_real(stage).view(self.world, -1),
+                                  torch.view_as_real(send).view(self.world, -1), self.group)
+                if f.pruned:      # inner layout [kz][ky]
+                    src = stage.view(self.world, f.mxl, nsh, f.kz, f.kyl).permute(1, 2, 3, 0, 4)
+                    send.view(f.mxl, nsh, f.kz, self.world, f.kyl).copy_(src)
+                else:             # inner layout [ky][kz]
+                    src = stage.view(self.world, f.mxl, nsh, f.kyl, f.kz).permute(1, 2, 0, 3, 4)
+                    send.view(f.mxl, nsh, self.world, f.kyl, f.kz).copy_(src)
+            self.backend.shells_yz(nsh, xcols, planes2d, out[s0:s1])
 
     # -- contraction ---------------------------------------------------------- #
     def contract(self, fields, rows, job_off=((0, 0, 0),), marks=None, on_device=False):
@@ -564,6 +631,19 @@ class Engine:
         self.backend.close()
         if self.device.type == "cuda":
             torch.cuda.empty_cache()      # hand the (often multi-GB) scratch back to the driver
+
+
+def all_to_all_blocks(out, inp, group=None):
+    """out[r] = block `rank` of rank r's inp (dim 0 split in `world` equal blocks): NCCL all-to-all;
+    falls back to a list all-to-all where the backend has no single-tensor form."""
+    try:
+        dist.all_to_all_single(out, inp.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):
+        world = dist.get_world_size(group)
+        outs = [t.contiguous() for t in out.chunk(world, dim=0)]
+        dist.all_to_all(outs, [t.contiguous() for t in inp.chunk(world, dim=0)], group=group)
+        for dst, t in zip(out.chunk(world, dim=0), outs):
+            dst.copy_(t)
 
 
 def all_gather_concat(out, inp, group=None):
@@ -676,6 +756,10 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
             cur_bins = new_bins
         if cur:
             batches.append(np.asarray(cur))
+    # one field table for all batches, sized for the largest: allocating (and releasing) tens of GiB per
+    # batch costs more than the synthesis of a shell, and a cached block of another size cannot be reused
+    max_nb = max(len(np.unique(uniq[b])) for b in batches)
+    big_table = _alloc_table((nseg * max_nb, engine.ncells), engine) if max_nb <= seg_cap else None
     for batch in batches:
         tri = uniq[batch]
         bins = np.unique(tri)
@@ -687,7 +771,7 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
             raise MemoryError(f"one triangle needs {nseg * nb} resident shell fields of "
                               f"{engine.ncells * engine.itemsize / 2**30:.1f} GiB each; only "
                               f"{engine.row_capacity()} fit on this device (use grid='auto' or more GPUs)")
-        table = _alloc_table((nseg * nb, engine.ncells), engine)
+        table = big_table[:nseg * nb]
         fields = []
         for sidx in range(nseg):
             for run in _runs(bins.tolist()):
@@ -719,6 +803,7 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
         else:
             pending.append((batch, engine.contract(fields, rows, job_off, marks=marks, on_device=True)))
         del table, fields
+    del big_table
     engine.last_batches = len(batches)
 
     def fetch():

@@ -66,7 +66,11 @@ typedef struct bsk_geometry {
   int32_t no_prune;  /* 1 = always use the generic cuFFT 2-D c2r path (debug / A-B timing);
                         0 = use the pruned y pass + fused z-pass kernel when neval is a
                         power of two in [64, 2048] and fft_precision is F64 */
-  int32_t reserved;
+  int32_t transposed;/* 1 = the spectrum cube is distributed in ky blocks (y-slabs) and the exchanges
+                        around the x transforms are all-to-all transposes, the pfft scheme the
+                        reference relies on (main.py:1612, every mesh.paint / c2r); for spectra
+                        that cannot be cropped (2*ncrop+1 >= nmesh).  0 = every rank holds the whole
+                        cropped cube (all-gather of the cropped planes) */
 } bsk_geometry;
 
 /* Derived sizes, bsk_plan_info(): counts in ELEMENTS (complex counts are numbers of
@@ -87,6 +91,11 @@ typedef struct bsk_info {
   int64_t planes2d_complex_per_shell;/* mxl * M * (M/2+1), or mxl * M * kz on the pruned path */
   int64_t field_real_per_shell;     /* mxl * M * M = local cells */
   int64_t fft_work_bytes;      /* cuFFT work areas owned by the plan */
+  int64_t kyl, ky0;            /* ky block of this rank's part of the cube: [ky0, ky0+kyl); kyl == ky
+                                  unless the plan is transposed.  Then planes_all = N * kyl * kz,
+                                  cube = kx * kyl * kz and xcols per shell = M * kyl * kz */
+  int64_t xplanes_complex_per_shell; /* transposed plans: mxl * ky * kz, the buffer bsk_shells_yz reads */
+  int64_t pruned;              /* 1: pruned y pass + fused z pass (inner layout of xcols / xplanes is [kz][ky]) */
 } bsk_info;
 
 int bsk_version(void);
@@ -144,6 +153,17 @@ int bsk_modes_per_bin(bsk_plan* plan, int nbins, const double* lo, const double*
 int bsk_shells_prepare(bsk_plan* plan, int nsh);
 int bsk_shells(bsk_plan* plan, const void* cube, int kind, double kpow, int nsh,
                const double* lo, const double* hi, void* xcols, void* planes2d, void* fields);
+/* The two halves of bsk_shells() for transposed plans (the distributed c2r of main.py:1859-1861 as
+ * pfft does it): bsk_shells_x filters this rank's ky block of the cube and runs the inverse x
+ * transform -> xcols [M][nsh][kyl][kz] ([M][nsh][kz][kyl] on the pruned path, fft_precision complex);
+ * the host then transposes with one all-to-all (chunk r of the x axis goes to rank r, the ky blocks
+ * are concatenated in rank order) into xplanes [mxl][nsh][ky][kz] ([mxl][nsh][kz][ky] pruned), and
+ * bsk_shells_yz finishes the (y,z) transforms of this rank's planes into fields [nsh][mxl*M*M].
+ * Likewise bsk_forward_finish() of a transposed plan takes planes_all = [N][kyl][kz]: the planes of
+ * bsk_forward_local() after the all-to-all that sends ky block r to rank r. */
+int bsk_shells_x(bsk_plan* plan, const void* cube, int kind, double kpow, int nsh, const double* lo,
+                 const double* hi, void* xcols);
+int bsk_shells_yz(bsk_plan* plan, int nsh, const void* xplanes, void* planes2d, void* fields);
 
 /* Triangle contraction schedule for a list of triangles given as TILE-ROW
  * triples: rows[t] = (r1, r2, r3) indexes the array of field pointers handed to

@@ -773,3 +773,69 @@ def test_bigfile_mesh_source(bk, syn, tmp_path):
     assert_b_close(got, orc.measure_unnormalized([mesh], syn.BOX, edges, idx))
     fb.close()
     fa.close()
+
+
+# --- un-croppable spectra: ky-block distributed cube, all-to-all transposes (north_star; pfft under
+#     the reference, main.py:1612 / 1859-1861) ------------------------------------------------------ #
+@pytest.mark.parametrize("n,dtype,tol", [(16, np.float64, 1e-10), (64, np.float32, 1e-5)])
+def test_transposed_split_path_single_gpu(bk, syn, monkeypatch, n, dtype, tol):
+    """BSKIT_B200_EXCHANGE=alltoall forces the transposed plan on one GPU: bsk_shells_x + bsk_shells_yz
+    (generic 16^3 layout and pruned 64^3 layout) must reproduce the oracle like bsk_shells does."""
+    bk.clear_cache()
+    monkeypatch.setenv("BSKIT_B200_EXCHANGE", "alltoall")
+    kf = syn.KF
+    mesh = syn.lognormal_mesh(n, seed=4, dtype=dtype)
+    kmin, kmax, dk = 0.5 * kf, 0.5 * kf + (n // 2 - 1 + 0.5) * kf, kf       # bins up to Nyquist
+    fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, triangle_type="equilateral")
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_equilateral(edges)
+    got = fb.measure_bispectrum_faster(0, len(idx))
+    e = [x for x in fb._meas().session._engines.values() if x.grid.full and x.precision == (1 if dtype == np.float64 else 0)][-1]
+    assert e.transposed and e.info.kyl == n and bool(e.info.pruned) == (n == 64)
+    assert np.array_equal(e.backend.modes_per_bin(edges[:, 0], edges[:, 1]), orc.modes_per_bin(n, syn.BOX, edges))
+    want = orc.measure_unnormalized([mesh.astype(np.float64)], syn.BOX, edges, idx)
+    assert_b_close(got["B"], want, tol, 1e-12 if dtype == np.float64 else 1e-6)
+    gi = fb.measure_gridinfo_faster(0, len(idx))
+    wn, _ = orc.measure_gridinfo(n, syn.BOX, edges, idx)
+    assert np.array_equal(gi["N_tri"], np.rint(wn))
+    fb.close()
+    bk.clear_cache()
+
+
+def test_two_gpu_all_to_all_matches_oracle(bk, syn, tmp_path):
+    """Two real GPUs, bins up to Nyquist: the spectrum is distributed in ky blocks and both exchanges are
+    NCCL all-to-all transposes.  Skipped on a single-GPU box (gloo coverage: tests/test_multirank_gloo.py)."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 64
+    script = tmp_path / "a2a.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bskit_b200 as bk\nfrom bskit_b200 import synthetic as syn\n"
+        "lr = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(lr)\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', lr))\n"
+        f"n = {n}; kf = syn.KF; kmin, kmax, dk = 0.5 * kf, 0.5 * kf + (n // 2 - 1 + 0.5) * kf, kf\n"
+        "mesh = syn.lognormal_mesh(n, seed=4)\n"
+        "fb = bk.FFTBispectrum(mesh, BoxSize=syn.BOX, kmin=kmin, kmax=kmax, dk=dk, triangle_type='equilateral', device=torch.device('cuda', lr))\n"
+        "b = fb.measure_bispectrum_faster(0, 10**9)['B']; g = fb.measure_gridinfo_faster(0, 10**9)\n"
+        "e = [x for x in fb._meas().session._engines.values() if x.grid.full][-1]\n"
+        "assert e.transposed and e.info.kyl == n // 2\n"
+        f"if dist.get_rank() == 0: np.savez({str(tmp_path / 'out.npz')!r}, B=b, N=g['N_tri'])\n"
+        "dist.destroy_process_group()\n")
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)])
+    out = np.load(tmp_path / "out.npz")
+    kf = syn.KF
+    kmin, kmax, dk = 0.5 * kf, 0.5 * kf + (n // 2 - 1 + 0.5) * kf, kf
+    edges = orc.bin_edges(kmin, kmax, dk)
+    _, idx = orc.triangles_equilateral(edges)
+    mesh = syn.lognormal_mesh(n, seed=4)
+    want = orc.measure_unnormalized([mesh.astype(np.float64)], syn.BOX, edges, idx)
+    assert_b_close(out["B"], want, 1e-5, 1e-6)
+    wn, _ = orc.measure_gridinfo(n, syn.BOX, edges, idx)
+    assert np.array_equal(out["N"], np.rint(wn))

@@ -16,13 +16,13 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 
-def _worker(rank, world, init_file, grid_policy, outdir):
+def _worker(rank, world, init_file, grid_policy, outdir, nb=4):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
     from bskit_b200 import engine as eng, synthetic as syn
     from fake_backend import FakeBackend
-    n, nb = 16, 4
+    n = 16
     kmin, kmax, dk = syn.bench_bins(nb)
     from bskit_b200 import generate_bin_edge_list, generate_triangle_bin_list
     edges = generate_bin_edge_list(kmin, kmax, dk)
@@ -31,6 +31,10 @@ def _worker(rank, world, init_file, grid_policy, outdir):
     g = eng.choose_grid(n, syn.BOX, edges[:, 1].max(), grid_policy, world)
     e = eng.Engine(g, syn.BOX, 1, device=torch.device("cpu"), backend_cls=FakeBackend)
     assert e.world == world and e.info.nxl == n // world
+    assert e.transposed == bool(g.full and world > 1)
+    if e.transposed:      # exact mode counts are a collective over the ky blocks
+        from oracle import bskit_oracle as orc
+        assert np.array_equal(e.backend.modes_per_bin(edges[:, 0], edges[:, 1]), orc.modes_per_bin(n, syn.BOX, edges))
     cube = e.forward(mesh)                                   # full mesh given: each rank slices
     cube2 = e.forward(mesh[e.info.nx0:e.info.nx0 + e.info.nxl])   # or the local slab directly
     assert torch.equal(cube, cube2)
@@ -43,14 +47,16 @@ def _worker(rank, world, init_file, grid_policy, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,policy", [(2, "full"), (2, "auto"), (4, "full")])
-def test_sharded_pipeline_matches_oracle(world, policy):
+# nb = 7: bins up to 7.5 k_f on a 16^3 mesh -> nothing can be cropped -> the spectrum is distributed in
+# ky blocks and both exchanges are all-to-all transposes (engine.Engine.transposed)
+@pytest.mark.parametrize("world,policy,nb", [(2, "full", 4), (2, "auto", 4), (4, "full", 4), (2, "full", 7), (4, "auto", 7)])
+def test_sharded_pipeline_matches_oracle(world, policy, nb):
     from oracle import bskit_oracle as orc
     from bskit_b200 import synthetic as syn
     with tempfile.TemporaryDirectory() as d:
         init = os.path.join(d, "rendezvous")
-        mp.spawn(_worker, args=(world, init, policy, d), nprocs=world, join=True)
-        n, nb = 16, 4
+        mp.spawn(_worker, args=(world, init, policy, d, nb), nprocs=world, join=True)
+        n = 16
         kmin, kmax, dk = syn.bench_bins(nb)
         edges = orc.bin_edges(kmin, kmax, dk)
         _, idx = orc.triangles_all(edges, 1)
