@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--oracle-shells", default="",
                     help="comma separated k-bin indices: rank 0 gathers the mesh to the host, builds these shells with "
                          "the float64 oracle on the full grid and checks every closed triangle among them (large grids)")
+    ap.add_argument("--scheme", default="kf", choices=["kf", "paper80"],
+                    help="paper80: the reference's production binning (examples/batch/sub_measure_bs_faster_ill.sh:33-37): "
+                         "40 bins of width k_f from k_f/2, then bins of width 6 k_f up to 280.51 k_f (80 bins, 24138 triangles)")
     ap.add_argument("--profile", action="store_true",
                     help="only the full-grid device-resident steps (for ncu); prints stage times")
     return ap.parse_args()
@@ -262,13 +265,21 @@ def main():
 
     from bskit_b200 import synthetic as syn
     import bskit_b200 as bk
-    kmin, kmax, dk = syn.bench_bins(nbins)
-    edges = bk.generate_bin_edge_list(kmin, kmax, dk)
-    triples = bk.generate_triangle_bin_list(kmin, kmax, dk, return_indices=True)
+    if args.scheme == "paper80":
+        kf = 2.0 * np.pi / syn.BOX
+        kmin, kmax, dk = 0.5 * kf, 280.51 * kf, kf
+        edges = bk.generate_bin_edge_list(kmin, kmax, dk, 40, 6.0 * kf)
+        triples = bk.generate_triangle_bin_list(kmin, kmax, dk, num_lowk_bins=40, dk_high=6.0 * kf, return_indices=True)
+        binning = "k-bins: 40 of width k_f from k_f/2, then width 6 k_f up to 280.5 k_f (the reference's production scheme)"
+    else:
+        kmin, kmax, dk = syn.bench_bins(nbins)
+        edges = bk.generate_bin_edge_list(kmin, kmax, dk)
+        triples = bk.generate_triangle_bin_list(kmin, kmax, dk, return_indices=True)
+        binning = "k-bins of width k_f from k_f/2"
     ntri = len(triples)
     cores = host_cores()
     config = {"workload": f"{nmesh}^3 float32 lognormal mesh (seed 1, BoxSize 1000), S={len(edges)} "
-                          f"k-bins of width k_f from k_f/2, all {ntri} triangles, auto + normalisation",
+                          f"{binning}, all {ntri} triangles, auto + normalisation",
               "nmesh": nmesh, "nbins": int(len(edges)), "ntriangles": int(ntri),
               "parallelism": f"x-slab x{max(world, 1)}", "l2": "inputs larger than L2 (no flush needed)"}
 
@@ -335,9 +346,16 @@ def main():
     def device_slab(e_data):
         """This rank's x-planes of a lognormal-like field generated on the GPU (large grids: no host mesh)."""
         f = e_data.info
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(1234 + int(f.nx0))
-        g = torch.randn((int(f.nxl), nmesh, nmesh), generator=gen, device=dev, dtype=torch.float32)
+        # seeded per block of nmesh/8 planes, so the mesh does not depend on the number of ranks
+        blk = max(1, nmesh // 8)
+        parts = []
+        for x0 in range(int(f.nx0), int(f.nx0 + f.nxl), blk):
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(1234 + x0)
+            parts.append(torch.randn((min(blk, int(f.nx0 + f.nxl) - x0), nmesh, nmesh), generator=gen, device=dev,
+                                     dtype=torch.float32))
+        g = torch.cat(parts) if len(parts) > 1 else parts[0]
+        del parts
         # smooth along z and y (cheap separable box filter) so that low-k shells carry signal, then lognormal
         for dim in (1, 2):
             g = (g + torch.roll(g, 1, dim) + torch.roll(g, -1, dim)) / 3.0

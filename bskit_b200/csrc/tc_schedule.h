@@ -123,7 +123,7 @@ inline void unit_spans(const Placement& pl, const std::vector<Piece>& pcs, int l
 // one after the other (kGenCycles each, whatever the number of pieces in the unit), the MMA
 // issuers need 12 MMAs of max(11, N/2) cycles per unit; + a penalty when a unit is wider than one
 // MMA or the units of a team need more than its accumulator columns.
-constexpr double kGenCycles = 450.0;
+constexpr double kGenCycles = 450.0, kReloadCycles = 50.0;
 inline double placement_cost(const Placement& pl, const std::vector<Piece>& pcs, bool* feasible = nullptr) {
   int lo[kUnits], n[kUnits];
   unit_spans(pl, pcs, lo, n);
@@ -141,7 +141,23 @@ inline double placement_cost(const Placement& pl, const std::vector<Piece>& pcs,
     if (sum > kTeamCols) { ok = false; penalty += 1000.0 + 10.0 * (sum - kTeamCols); }
   }
   if (feasible) *feasible = ok;
-  const double gen = kGenCycles * std::max(team_units[0], team_units[1]);
+  // a warp slot whose host group changes from one unit to the next reloads its resident row there
+  // (8 more 128-bit loads for that warp): the unit takes about kReloadCycles longer
+  double reload[kTeams] = {0.0, 0.0};
+  for (int t = 0; t < kTeams; ++t)
+    for (int j = 1; j < kUpt; ++j) {
+      bool any = false;
+      for (int q = 0; q < 4; ++q) {
+        const int pi = pl.pos[t * 4 + q][j];
+        if (pi < 0) continue;
+        int prev = -1;
+        for (int jj = j - 1; jj >= 0 && prev < 0; --jj)
+          if (pl.pos[t * 4 + q][jj] >= 0) prev = pcs[pl.pos[t * 4 + q][jj]].host;
+        any |= prev >= 0 && prev != pcs[pi].host;
+      }
+      if (any) reload[t] += kReloadCycles;
+    }
+  const double gen = std::max(kGenCycles * team_units[0] + reload[0], kGenCycles * team_units[1] + reload[1]);
   return std::max(gen, 12.0 * mma) + 0.05 * (gen + 12.0 * mma) + penalty;
 }
 
@@ -185,10 +201,9 @@ inline bool place_pass(const std::vector<std::pair<int, int>>& cls,
       int bw = -1, bj = -1, bkey = 1 << 30;
       for (int w = 0; w < kWarpSlots; ++w) {
         const int h = slot_host(pl, pcs, w);
-        if (h != -1 && h != pcs[pi].host) continue;
         for (int j = 0; j < kUpt; ++j)
           if (pl.pos[w][j] < 0) {
-            const int key = j * 64 + (h == -1 ? 32 : 0) + (int)(rnd.next() & 15);
+            const int key = j * 64 + (h == -1 ? 32 : (h != pcs[pi].host ? 48 : 0)) + (int)(rnd.next() & 15);
             if (key < bkey) { bkey = key; bw = w; bj = j; }
             break;
           }
@@ -211,16 +226,7 @@ inline bool place_pass(const std::vector<std::pair<int, int>>& cls,
         const int p1 = pl.pos[w1][j1], p2 = pl.pos[w2][j2];
         if (p1 < 0 && p2 < 0) continue;
         std::swap(pl.pos[w1][j1], pl.pos[w2][j2]);
-        bool legal = true;
-        for (int w : {w1, w2}) {
-          int h = -1;
-          for (int j = 0; j < kUpt; ++j)
-            if (pl.pos[w][j] >= 0) {
-              if (h == -1) h = pcs[pl.pos[w][j]].host;
-              else legal &= pcs[pl.pos[w][j]].host == h;
-            }
-        }
-        const double c = legal ? placement_cost(pl, pcs) : 1e300;
+        const double c = placement_cost(pl, pcs);
         if (c <= cur) cur = c; else std::swap(pl.pos[w1][j1], pl.pos[w2][j2]);
       } else {                           // exchange two whole warp slots (changes the teams)
         if (w1 == w2) continue;
