@@ -300,6 +300,13 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
       have = true;
     }
   }
+  // A team with exactly two units alternates their order from chunk to chunk (even chunks: unit 1
+  // first): a unit whose window closes is then the FIRST of its chunk and the second of the next, so
+  // two unit slots instead of one separate the last MMA of a window from the first of the next and the
+  // drain (TMEM reads: 64 B/cycle/SM) no longer stalls the in-order issuer.  Issuer and generator
+  // compute the same order; the drain only depends on which unit closes after which chunk.
+  const bool alt = my_nu == 2;
+  const bool same01 = __all_sync(0xffffffffu, ra_off[0] == ra_off[1]);   // alt: resident row shared by both units
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint32_t a_tmem0 = tbase + lane_sel + TM_A + (uint32_t)team * 128u;
   const uint32_t bar_afull = bars + (A_FULL + team * 2) * 8, bar_aempty = bars + (A_EMPTY + team * 2) * 8;
@@ -330,23 +337,30 @@ __device__ __forceinline__ void team_loop(const Params& p, const unsigned char* 
     for (int c = 0; c < NCH; ++c) {
       const uint32_t cbase = raw + c * (CH * 4);
       float4 own[CH / 4];
+      bool have_own = false;      // alt teams: the resident row of this chunk is in registers
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j < my_nu) {
+          // unit executed in slot j of this chunk, and its (warp-uniform) flags and (per-lane) row offsets
+          const bool swp = alt && !(c & 1);
+          const uint32_t ra_j = j < 2 && swp ? ra_off[j ^ 1] : ra_off[j], rb_j = j < 2 && swp ? rb_off[j ^ 1] : rb_off[j];
+          const bool idle_j = j < 2 && swp ? idle[j ^ 1] : idle[j];
+          const bool reload_j = alt ? (!have_own || !same01) : reload[j];
           const uint32_t ab = n_gen & 1u;
           const uint32_t a_tmem = a_tmem0 + ab * 64u;
           const uint32_t ok = mbar_test(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
-          if (idle[j]) {
+          if (idle_j) {
             hand_over();
             if (!ok) tc_wait(bar_aempty + ab * 8, ((n_gen >> 1) & 1u) ^ 1u);
           } else {
-            if (reload[j]) {
+            if (reload_j) {
 #pragma unroll
-              for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + ra_off[j] + v4 * 16);
+              for (int v4 = 0; v4 < CH / 4; ++v4) own[v4] = lds128(cbase + ra_j + v4 * 16);
+              have_own = true;
             }
 #pragma unroll
             for (int h = 0; h < 4; ++h) {   // 8 cells at a time
-              const float4 b0 = lds128(cbase + rb_off[j] + h * 32), b1 = lds128(cbase + rb_off[j] + h * 32 + 16);
+              const float4 b0 = lds128(cbase + rb_j + h * 32), b1 = lds128(cbase + rb_j + h * 32 + 16);
               const float4 a0 = own[2 * h], a1 = own[2 * h + 1];
               const float2 pa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
               const float2 pb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
@@ -530,9 +544,6 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
   // (per-unit constants are read from the parameter bank where they are used: the issuer runs on 48 registers)
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t gtot = (uint32_t)(my_tiles * NCH);
-  uint32_t nwin[UPT];
-#pragma unroll
-  for (int j = 0; j < UPT; ++j) nwin[j] = 0;
   uint32_t n_unit = 0, g = 0;
   long long m_afull = 0, m_dempty = 0, m_issue = 0, m_bfull = 0, m_mark = 0, m_start = 0;
   if constexpr (PROF) m_start = clock64();
@@ -552,22 +563,23 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         if (j >= my_nu) continue;
-        const int u = team * UPT + j;
+        const int jj = (my_nu == 2 && !(c & 1)) ? (j ^ 1) : j;      // the generators' unit order (team_loop)
+        const int u = team * UPT + jj;
         const uint32_t n = n_unit++;
         const uint32_t ab = n & 1u;
         if constexpr (PROF) m_mark = clock64();
         nbar_sync(1 + team * 2 + (int)ab, 160);
         if constexpr (PROF) { const long long now = clock64(); m_afull += now - m_mark; m_mark = now; }
         const bool opens = win_opens(g, u);
-        if (opens && nwin[j] > 0)    // first chunk of a window: the unit's accumulator must have been drained
+        if (opens && g > 0)    // first chunk of a later window: the unit's accumulator must have been drained
           nbar_sync(5 + u, 160);
         tc_fence_after();
         if constexpr (PROF) { const long long now = clock64(); m_dempty += now - m_mark; m_mark = now; }
-        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + (uint32_t)p.ublk0[team * UPT + j] * 8u;
+        const uint32_t d = tbase + TM_D + (uint32_t)team * TEAMCOLS + (uint32_t)p.ublk0[u] * 8u;
         const uint32_t a = tbase + TM_A + (uint32_t)team * 128u + ab * 64u;
-        const uint32_t id = make_idesc_tf32(p.uncol[team * UPT + j]);
+        const uint32_t id = make_idesc_tf32(p.uncol[u]);
         // first column of the unit (= 16-byte units into an image group) + the chunk's 4-cell groups
-        const uint32_t o0 = (uint32_t)p.ucol0[team * UPT + j] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
+        const uint32_t o0 = (uint32_t)p.ucol0[u] + (uint32_t)(c * (CH / 4)) * (uint32_t)N;
         const bool closes = win_closes(g, u, gtot);
         if (leader) {
 #pragma unroll
@@ -580,7 +592,6 @@ __device__ __forceinline__ void mma_loop(const Params& p, const unsigned char* s
           tc_commit(bars + (A_EMPTY + team * 2 + ab) * 8);
           if (closes) tc_commit(bars + (D_FULL + u) * 8);
         }
-        if (closes) ++nwin[j];
         __syncwarp();
         if constexpr (PROF) { const long long now = clock64(); m_issue += now - m_mark; m_mark = now; }
       }

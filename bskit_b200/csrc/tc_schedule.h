@@ -265,6 +265,150 @@ inline bool place_pass(const std::vector<std::pair<int, int>>& cls,
 
 }  // namespace detail
 
+// "Two halves" schedule for lists over <= 40 rows (one column window): the rows are cut into a low and
+// a high half; every sorted triangle a <= b <= c has its two smallest rows in the low half (pair (a,b),
+// column c, team 0) or its two largest in the high half (pair (b,c), column a, team 1) -- pigeonhole.
+// Only pairs WITHIN a half are generated: 2 * 210 instead of 820 for 40 rows, which is fewer than any
+// cover by 8-row group classes (436 needed rows on 640 lanes) and fits 2 + 2 units, so both teams work
+// through two units per chunk instead of three and two.
+//   A lane pair (2m, 2m+1) is a "slot": its lanes keep the two rows of a ROW PAIR (2t, 2t+1) in registers
+// for the whole chunk and meet ONE partner row per unit, which both lanes read (2-cycle shared-memory
+// loads).  A slot use (t, y) covers the pairs (2t, y) and (2t+1, y).  Row pairs t != u are related through
+// up to two uses on either side; the side with the lighter load takes them.
+inline bool build_schedule_halves(int ntri, const int32_t* rows, int nrows, Schedule& out) {
+  using namespace detail;
+  if (ntri < 256 || nrows < 4 || nrows > 8 * kMaxColGroups) return false;
+  const int nraw = (nrows + 7) / 8 * 8;
+  int h = (nraw / 2) & ~1;                    // rows [0, h) | [h, nraw)
+  out.passes.clear();
+  out.est_cycles = 0.0;
+  out.cover = true;
+  out.tri_slot.assign((size_t)ntri, -1);
+  out.pass_stride = (int64_t)kCapTot * 128;
+  std::vector<int> ta((size_t)ntri), tb((size_t)ntri), tcol((size_t)ntri), tteam((size_t)ntri);
+  std::set<std::pair<int, int>> need[kTeams];
+  for (int t = 0; t < ntri; ++t) {
+    int r[3] = {rows[3 * t], rows[3 * t + 1], rows[3 * t + 2]};
+    std::sort(r, r + 3);
+    if (r[0] < 0 || r[2] >= nrows) return false;
+    if (r[1] < h) { ta[t] = r[0]; tb[t] = r[1]; tcol[t] = r[2]; tteam[t] = 0; }
+    else { ta[t] = r[1]; tb[t] = r[2]; tcol[t] = r[0]; tteam[t] = 1; }
+    need[tteam[t]].insert({ta[t], tb[t]});
+  }
+  Pass ps;
+  ps.nraw = nraw;
+  ps.rawrow.assign((size_t)nraw, -1);
+  for (int i = 0; i < nrows; ++i) ps.rawrow[i] = i;
+  ps.ncols = nraw;
+  for (int g = 0; g < nraw / 8; ++g) ps.colslot[g] = 8 * g;
+  const uint32_t zero_row = (uint32_t)nraw;
+  ps.lane_tab.assign((size_t)kUnits * 128, zero_row | (zero_row << 8));
+  std::map<std::pair<int, int>, std::pair<int, int>> where[kTeams];     // pair -> (unit, lane-in-unit)
+  for (int team = 0; team < kTeams; ++team) {
+    if (need[team].empty()) continue;
+    // uses[t] = partner rows the slots of row pair t have to meet
+    std::map<int, std::vector<int>> uses;
+    std::map<std::pair<int, int>, std::set<int>> rel_rows_lo, rel_rows_hi;   // relation (t<u): rows of t / of u involved
+    std::map<int, std::set<int>> within;
+    for (auto& pr : need[team]) {
+      const int t = pr.first / 2, u = pr.second / 2;
+      if (t == u) { within[t].insert(pr.first); within[t].insert(pr.second); if (pr.first != pr.second) within[t].insert(-1); }
+      else { rel_rows_lo[{t, u}].insert(pr.first); rel_rows_hi[{t, u}].insert(pr.second); }
+    }
+    std::map<int, int> load;
+    for (auto& kv : within) {
+      // pairs (2t,2t), (2t,2t+1), (2t+1,2t+1): partner 2t covers the first two, partner 2t+1 the last two
+      const int t = kv.first;
+      bool need00 = false, need01 = kv.second.count(-1) > 0, need11 = false;
+      for (auto& pr : need[team]) {
+        if (pr.first == 2 * t && pr.second == 2 * t) need00 = true;
+        if (pr.first == 2 * t + 1 && pr.second == 2 * t + 1) need11 = true;
+      }
+      if (need00 || (need01 && !need11)) uses[t].push_back(2 * t);
+      if (need11) uses[t].push_back(2 * t + 1);
+      load[t] = (int)uses[t].size();
+    }
+    // relations between different row pairs, heaviest first, to the lighter side
+    std::vector<std::pair<int, int>> rels;
+    for (auto& kv : rel_rows_lo) rels.push_back(kv.first);
+    std::stable_sort(rels.begin(), rels.end(), [&](const std::pair<int, int>& x, const std::pair<int, int>& y) {
+      return rel_rows_lo[x].size() + rel_rows_hi[x].size() > rel_rows_lo[y].size() + rel_rows_hi[y].size();
+    });
+    for (auto& r : rels) {
+      // own = t: one use per involved row of u (and vice versa)
+      const int cost_t = (int)rel_rows_hi[r].size(), cost_u = (int)rel_rows_lo[r].size();
+      const bool to_t = load[r.first] + cost_t < load[r.second] + cost_u ||
+                        (load[r.first] + cost_t == load[r.second] + cost_u && cost_t <= cost_u);
+      if (to_t) { for (int y : rel_rows_hi[r]) uses[r.first].push_back(y); load[r.first] += cost_t; }
+      else { for (int x : rel_rows_lo[r]) uses[r.second].push_back(x); load[r.second] += cost_u; }
+    }
+    // smallest number of units whose 64 slots hold every row pair's uses
+    int U = 0;
+    for (int cand = 1; cand <= kUpt && U == 0; ++cand) {
+      int slots = 0;
+      for (auto& kv : uses) slots += ((int)kv.second.size() + cand - 1) / cand;
+      if (slots <= 64 && cand * kMaxUnitCols <= kTeamCols + (cand == 2 ? 16 : 0)) U = cand;
+    }
+    if (U == 0 || U * kMaxUnitCols > kTeamCols + 16) BSK_TCS_FAIL("two halves: the pairs of a half do not fit a team");
+    ps.nu[team] = U;
+    int slot = 0;
+    for (auto& kv : uses) {
+      const int t = kv.first;
+      std::vector<int> list = kv.second;
+      std::sort(list.begin(), list.end());
+      const int nslots = ((int)list.size() + U - 1) / U;
+      for (int k = 0; k < nslots; ++k, ++slot) {
+        for (int j = 0; j < U; ++j) {
+          // unit j takes the j-th block of the sorted partner list: neighbouring columns share a unit
+          const int idx = j * nslots + k;
+          const int u = team * kUpt + j;
+          for (int e = 0; e < 2; ++e) {
+            const int lane = slot * 2 + e, own = 2 * t + e;
+            const uint32_t a_slot = own < nrows ? (uint32_t)own : zero_row;
+            const uint32_t b_slot = idx < (int)list.size() ? (uint32_t)list[idx] : zero_row;
+            ps.lane_tab[(size_t)u * 128 + lane] = a_slot | (b_slot << 8);    // idle uses keep the resident row
+            if (idx < (int)list.size() && own < nrows) {
+              const auto key = std::make_pair(std::min(own, list[idx]), std::max(own, list[idx]));
+              if (!where[team].count(key)) where[team][key] = {u, lane};
+            }
+          }
+        }
+      }
+    }
+    ps.pieces += U * ((slot + 15) / 16);
+  }
+  // unit column ranges from the triangles that really read them
+  int ulo[kUnits], uhi[kUnits];
+  for (int u = 0; u < kUnits; ++u) { ulo[u] = 1 << 30; uhi[u] = -1; }
+  for (int t = 0; t < ntri; ++t) {
+    auto wh = where[tteam[t]].find({ta[t], tb[t]});
+    if (wh == where[tteam[t]].end()) BSK_TCS_FAIL("two halves: pair without a lane");
+    ulo[wh->second.first] = std::min(ulo[wh->second.first], tcol[t]);
+    uhi[wh->second.first] = std::max(uhi[wh->second.first], tcol[t]);
+  }
+  for (int u = 0; u < kUnits; ++u) {
+    const bool live = (u % kUpt) < ps.nu[u / kUpt];
+    if (uhi[u] < 0) { ps.col0[u] = 0; ps.ncol[u] = live ? 8 : 0; }
+    else { ps.col0[u] = ulo[u] / 8 * 8; ps.ncol[u] = uhi[u] / 8 * 8 + 8 - ps.col0[u]; }
+    if (ps.ncol[u] > kMaxUnitCols) BSK_TCS_FAIL("two halves: unit wider than one MMA");
+    if (ps.ncol[u] > 0) ps.mma_cost += std::max(11, ps.ncol[u] / 2);
+  }
+  int tu[kTeams] = {0, 0};
+  for (int t = 0; t < kTeams; ++t) {
+    int b = 0;
+    for (int j = 0; j < kUpt; ++j) { ps.blk0[t * kUpt + j] = b; b += ps.ncol[t * kUpt + j] / 8; tu[t] += ps.ncol[t * kUpt + j] > 0; }
+    if (b * 8 > kTeamCols) BSK_TCS_FAIL("two halves: team needs more accumulator columns than it has");
+  }
+  for (int t = 0; t < ntri; ++t) {
+    const auto wh = where[tteam[t]][{ta[t], tb[t]}];
+    const int u = wh.first;
+    out.tri_slot[t] = (int64_t)((u / kUpt) * kTeamCols + ps.blk0[u] * 8 + tcol[t] - ps.col0[u]) * 128 + wh.second;
+  }
+  out.est_cycles = std::max(kGenCycles * std::max(tu[0], tu[1]), 12.0 * (double)ps.mma_cost) + 200.0;
+  out.passes.push_back(std::move(ps));
+  return true;
+}
+
 // Build the schedule; returns false when the list is not eligible (the caller then keeps the
 // FP32-pipe kernel).
 inline bool build_schedule_mode(int ntri, const int32_t* rows, int nrows, bool cover, Schedule& out) {
@@ -493,6 +637,12 @@ inline bool build_schedule(int ntri, const int32_t* rows, int nrows, Schedule& o
     if (force[0] == '1' && okb) pick_b = true;
   }
   out = pick_b ? std::move(b) : std::move(a);
+  // third candidate: the two-halves schedule (lists over <= 40 rows)
+  Schedule c;
+  const char* fh = getenv("BSK_TC_HALVES");              // A/B knob: 0 = never, 1 = whenever it is feasible
+  if (!(fh && fh[0] == '0') && build_schedule_halves(ntri, rows, nrows, c) &&
+      ((fh && fh[0] == '1') || c.est_cycles < out.est_cycles))
+    out = std::move(c);
   return true;
 }
 

