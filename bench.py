@@ -613,8 +613,9 @@ def main():
             "kernel_ms": t_contract * 1e3,
             "ncu": {k: ncu.get(k) for k in ("tensor_pipe_active_pct", "issue_active_pct", "smem_wavefront_pct",
                                             "local_load_requests", "kernel_ms")} if ncu else None,
-            "note": "bounded by the generator warps (pair products on the CUDA cores, latency bound at two "
-                    "generator warps per SM sub-partition), not by the tensor pipe: DESIGN.md section 3"}
+            "note": "bounded by the generation of the A operand (pair products on the CUDA cores, TMEM stores at "
+                    "~64 B/cycle per lane quarter, hand-over latency), not by the tensor pipe: DESIGN.md section 3, "
+                    "profiles/r2_tc_contract_history.md"}
     else:
         issued = full["cplan"]["nblocks"] * 80.0 * 2.0 * cells if full["cplan"] else None
         fp32_peak = 72.5e12 * clk / 1965.0        # scripts/dev/ffma_probe.cu at 1965 MHz (round 1)

@@ -351,31 +351,79 @@ inline bool build_schedule_halves(int ntri, const int32_t* rows, int nrows, Sche
     }
     if (U == 0 || U * kMaxUnitCols > kTeamCols + 16) BSK_TCS_FAIL("two halves: the pairs of a half do not fit a team");
     ps.nu[team] = U;
-    int slot = 0;
+    // slots: (row pair, partner row per unit); unit j takes the j-th block of the row pair's sorted
+    // partner list, so neighbouring columns share a unit
+    struct Slot { int t; int partner[kUpt]; };
+    std::vector<Slot> slots;
     for (auto& kv : uses) {
-      const int t = kv.first;
       std::vector<int> list = kv.second;
       std::sort(list.begin(), list.end());
       const int nslots = ((int)list.size() + U - 1) / U;
-      for (int k = 0; k < nslots; ++k, ++slot) {
-        for (int j = 0; j < U; ++j) {
-          // unit j takes the j-th block of the sorted partner list: neighbouring columns share a unit
-          const int idx = j * nslots + k;
-          const int u = team * kUpt + j;
-          for (int e = 0; e < 2; ++e) {
-            const int lane = slot * 2 + e, own = 2 * t + e;
-            const uint32_t a_slot = own < nrows ? (uint32_t)own : zero_row;
-            const uint32_t b_slot = idx < (int)list.size() ? (uint32_t)list[idx] : zero_row;
-            ps.lane_tab[(size_t)u * 128 + lane] = a_slot | (b_slot << 8);    // idle uses keep the resident row
-            if (idx < (int)list.size() && own < nrows) {
-              const auto key = std::make_pair(std::min(own, list[idx]), std::max(own, list[idx]));
-              if (!where[team].count(key)) where[team][key] = {u, lane};
-            }
+      for (int k = 0; k < nslots; ++k) {
+        Slot sl;
+        sl.t = kv.first;
+        for (int j = 0; j < kUpt; ++j) sl.partner[j] = (j < U && j * nslots + k < (int)list.size()) ? list[j * nslots + k] : -1;
+        slots.push_back(sl);
+      }
+    }
+    // Order of the slots over the 4 warps x 16 lane pairs: rows whose numbers agree modulo 8 start in the
+    // same shared-memory banks (row stride 132 words), so the 16 partner rows a warp reads in a unit
+    // should spread over the 8 residues, two each.  Random exchanges of slots, keeping what lowers the
+    // number of wavefronts (max multiplicity of a residue per warp and unit; the resident rows, read
+    // once per chunk, count likewise).
+    {
+      while ((int)slots.size() < 64) { Slot sl; sl.t = -1; for (int j = 0; j < kUpt; ++j) sl.partner[j] = -1; slots.push_back(sl); }
+      auto cost = [&]() {
+        int total = 0;
+        for (int w = 0; w < 4; ++w) {
+          for (int j = 0; j < U; ++j) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+            for (int k = 0; k < 16; ++k) { const int y = slots[w * 16 + k].partner[j]; if (y >= 0) mx = std::max(mx, ++cnt[y & 7]); }
+            total += 2 * mx;
+          }
+          int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+          std::set<int> seen;
+          for (int k = 0; k < 16; ++k) {
+            const int t = slots[w * 16 + k].t;
+            if (t < 0 || seen.count(t)) continue;          // lanes with the same row read the same chunk
+            seen.insert(t);
+            mx = std::max(mx, ++cnt[(2 * t) & 7]);
+            mx = std::max(mx, ++cnt[(2 * t + 1) & 7]);
+          }
+          total += mx;
+        }
+        return total;
+      };
+      Lcg rnd(4711u + (uint64_t)team);
+      int cur = cost();
+      for (int it = 0; it < 4000; ++it) {
+        const int x = rnd.below(64), y = rnd.below(64);
+        if (x / 16 == y / 16) continue;
+        std::swap(slots[x], slots[y]);
+        const int c = cost();
+        if (c <= cur) cur = c; else std::swap(slots[x], slots[y]);
+      }
+    }
+    int used = 0;
+    for (int slot = 0; slot < 64; ++slot) {
+      const Slot& sl = slots[slot];
+      if (sl.t < 0) continue;
+      ++used;
+      for (int j = 0; j < U; ++j) {
+        const int u = team * kUpt + j;
+        for (int e = 0; e < 2; ++e) {
+          const int lane = slot * 2 + e, own = 2 * sl.t + e;
+          const uint32_t a_slot = own < nrows ? (uint32_t)own : zero_row;
+          const uint32_t b_slot = sl.partner[j] >= 0 ? (uint32_t)sl.partner[j] : zero_row;
+          ps.lane_tab[(size_t)u * 128 + lane] = a_slot | (b_slot << 8);    // idle uses keep the resident row
+          if (sl.partner[j] >= 0 && own < nrows) {
+            const auto key = std::make_pair(std::min(own, sl.partner[j]), std::max(own, sl.partner[j]));
+            if (!where[team].count(key)) where[team][key] = {u, lane};
           }
         }
       }
     }
-    ps.pieces += U * ((slot + 15) / 16);
+    ps.pieces += U * ((used + 15) / 16);
   }
   // unit column ranges from the triangles that really read them
   int ulo[kUnits], uhi[kUnits];

@@ -752,9 +752,12 @@ def _batched_contract(engine: Engine, nseg, synth, job_seg_off, uniq, marks=None
     out = np.empty((njobs, len(uniq)))
     pending = []                 # (batch, device tensor): fetched at the end, or by the caller when deferred
     nbins_all = len(np.unique(uniq))
-    if engine.row_capacity() // nseg < nbins_all and engine.chunk > 1 and engine.max_rows is None:
+    if engine.row_capacity() // nseg < 1.3 * nbins_all and engine.chunk > 1 and engine.max_rows is None:
         engine.set_chunk(1)      # trade synthesis batching for field memory before cutting the list
-    seg_cap = max(1, engine.row_capacity() // nseg)       # distinct bins resident per segment
+    cap = engine.row_capacity()
+    if symmetric:        # the folded copy of the table lives next to it: 1/8 of it on one GPU, 1/4 on a slab
+        cap = int(cap / (1.16 if engine.world == 1 else 1.30))
+    seg_cap = max(1, cap // nseg)                          # distinct bins resident per segment
     if int(uniq.max()) + 1 <= seg_cap or len(np.unique(uniq)) <= seg_cap:
         batches = [np.arange(len(uniq))]              # the common case: everything is resident
     else:
