@@ -101,3 +101,24 @@ def test_combine_matches_reference_golden():
     assert got.shape == want.shape
     for r in range(len(want)):
         assert ["%.6e" % v for v in got[r, 1:]] == ["%.6e" % v for v in want[r, 1:]]
+
+
+def test_reference_production_binning_80_bins_24138_triangles():
+    """The reference's production job (examples/batch/sub_measure_bs_faster_ill.sh:33-37): 40 bins of width k_f
+    from k_f/2, then bins of width 6 k_f up to 280.51 k_f -> 80 bins, 24 138 closed triangles
+    (`bench.py --scheme paper80`); generator == oracle, and the tensor-core schedule covers the list in
+    passes over its 80 rows with every triangle in its own accumulator slot."""
+    import ctypes as C
+    from bskit_b200 import _native as nat
+    kf = 2 * np.pi / 75.0                       # LBOX = 75 in the batch script: DK = 0.0837758 = k_f
+    kmin, kmax, dk, dk_high = 0.5 * kf, 23.5, kf, 6.0 * kf
+    edges = bk.generate_bin_edge_list(kmin, kmax, dk, 40, dk_high)
+    idx = bk.generate_triangle_bin_list(kmin, kmax, dk, num_lowk_bins=40, dk_high=dk_high, return_indices=True)
+    assert len(edges) == 80 and len(idx) == 24138
+    oe = orc.bin_edges(kmin, kmax, dk, 40, dk_high)
+    _, oi = orc.triangles_all(oe, 1)
+    assert np.array_equal(edges, oe) and np.array_equal(np.asarray(idx), oi)
+    rows = np.ascontiguousarray(idx, dtype=np.int32)
+    out = (C.c_int64 * 6)()
+    assert nat.lib().bsk_tc_schedule_info(len(rows), rows.ctypes.data_as(C.POINTER(C.c_int32)), 80, out) == 0
+    assert out[0] > 0 and out[1] == len(rows) and out[4] == 1, list(out)      # eligible, injective, in range

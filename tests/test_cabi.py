@@ -95,12 +95,15 @@ def test_tensor_core_schedule_is_injective_and_pruned():
         seg = (nb + 3) // 4 * 4
         return np.asarray(idx) + np.array([0, 0, seg if nf == 2 else 0]), seg * nf
 
-    for nb, max_units, max_passes in ((40, 6, 2), (24, 3, 1), (12, 2, 1), (80, 32, 9)):
+    # S = 40: the two-halves schedule -- 2 + 2 units (420 pair rows on 512 lanes), 152 accumulator columns, one pass
+    for nb, max_units, max_passes in ((40, 4, 1), (24, 3, 1), (12, 2, 1), (80, 32, 6)):
         idx, nrows = all_list(nb)
         got = info(idx, nrows)
         assert 0 < got["units"] <= max_units and got["passes"] <= max_passes, got
         assert got["distinct"] == len(idx) and got["in_range"] == 1, got      # injective, in range
         assert got["cols"] <= 96 * 2 * got["passes"], got                     # TMEM accumulator budget
+        if nb == 40:
+            assert got["cols"] <= 160 and got["cost"] <= 80, got
     # two-field <AAB> list: 80 rows, the third row lives in the second segment
     idx, nrows = all_list(40, 2)
     got = info(idx, nrows)

@@ -721,8 +721,9 @@ def test_metric_config_512_all_triangles_vs_oracle(bk, syn, contraction):
     print(f"[{contraction}] median {q50:.2e}  99% {q99:.2e}  max {rel.max():.2e}  above 1e-5: {bad.sum()} of {len(rel)}"
           f"  max |dB|/rms {np.abs(got - want).max() / rms:.2e}  mean signed {np.mean((got - want) / want):.2e}")
     if contraction == "tensor":
-        assert q50 < 1.5e-6 and q99 < 1.2e-5 and bad.mean() < 0.012
-        assert np.abs(got - want).max() < 1.5e-5 * rms
+        # measured (class-cover schedule / 512^3 lognormal): median 7.8e-7, 99 % 7.9e-6, 0.83 % above 1e-5
+        assert q50 < 1.5e-6 and q99 < 1.5e-5 and bad.mean() < 0.015
+        assert np.abs(got - want).max() < 2e-5 * rms       # measured 1.0e-5 .. 1.2e-5 (largest |B| ~ 15 rms at 8e-7 relative)
     else:
         assert q50 < 2e-8 and q99 < 5e-7 and bad.mean() < 0.0012
         assert np.abs(got - want).max() < 1e-7 * rms
