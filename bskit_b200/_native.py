@@ -21,7 +21,7 @@ EXPORTS = (
     "bsk_version", "bsk_last_error", "bsk_plan_create", "bsk_plan_destroy", "bsk_plan_info",
     "bsk_set_compensation", "bsk_plan_set_stream", "bsk_fold_even", "bsk_forward_local", "bsk_forward_finish", "bsk_modes_per_bin", "bsk_shells_x", "bsk_shells_yz",
     "bsk_shells", "bsk_shells_prepare", "bsk_cplan_create", "bsk_cplan_destroy", "bsk_cplan_info", "bsk_cplan_set_path",
-    "bsk_cplan_path", "bsk_tc_schedule_info", "bsk_contract",
+    "bsk_cplan_path", "bsk_tc_schedule_info", "bsk_tc_schedule_eval", "bsk_contract",
     "bsk_reduce_list", "bsk_paint_cic", "bsk_launch_count",
 )
 
@@ -79,6 +79,7 @@ def lib():
     L.bsk_cplan_set_path.argtypes = [vp, ip]
     L.bsk_cplan_path.argtypes = [vp, C.POINTER(C.c_int64)]
     L.bsk_tc_schedule_info.argtypes = [ip, C.POINTER(C.c_int32), ip, C.POINTER(C.c_int64)]
+    L.bsk_tc_schedule_eval.argtypes = [ip, C.POINTER(C.c_int32), ip, C.c_int64, dp, dp]
     L.bsk_contract.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     L.bsk_reduce_list.argtypes = [C.POINTER(vp), ip, ip, C.c_int64, ip, C.POINTER(C.c_int32), dp, vp]
     L.bsk_paint_cic.argtypes = [vp, ip, C.c_int64, ip, dp, vp, vp]

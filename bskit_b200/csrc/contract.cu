@@ -745,6 +745,47 @@ int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6
   return BSK_OK;
 }
 
+int bsk_tc_schedule_eval(int ntri, const int32_t* rows, int nrows, int64_t ncells, const double* fields,
+                         double* sums) {
+  using namespace bsk::tc;
+  BSK_REQUIRE(rows && fields && sums && ntri > 0 && nrows > 0 && ncells > 0, "bsk_tc_schedule_eval: bad argument");
+  for (int i = 0; i < 3 * ntri; ++i)
+    BSK_REQUIRE(rows[i] >= 0 && rows[i] < nrows, "bsk_tc_schedule_eval: row index %d outside [0,%d)", rows[i], nrows);
+  bsk::tcs::Schedule sc;
+  BSK_REQUIRE(bsk::tcs::build_schedule(ntri, rows, nrows, sc), "bsk_tc_schedule_eval: list not eligible for the tensor-core path");
+  // the partial sums the kernel would hold, [pass][team][TEAMCOLS][128], computed the way the kernel
+  // routes data: lane (a_slot, b_slot) -> pair product, window column -> raw slot -> field row
+  std::vector<double> partial(sc.passes.size() * (size_t)sc.pass_stride, 0.0);
+  std::vector<double> zero((size_t)ncells, 0.0);
+  for (size_t ip = 0; ip < sc.passes.size(); ++ip) {
+    const auto& ps = sc.passes[ip];
+    auto raw = [&](int slot) -> const double* {
+      if (slot < 0 || slot >= ps.nraw || ps.rawrow[slot] < 0) return zero.data();     // slot nraw is the zero row
+      return fields + (size_t)ps.rawrow[slot] * (size_t)ncells;
+    };
+    for (int t = 0; t < NTEAMS; ++t)
+      for (int j = 0; j < ps.nu[t]; ++j) {
+        const int u = t * UPT + j;
+        for (int l = 0; l < 128; ++l) {
+          const uint32_t e = ps.lane_tab[(size_t)u * 128 + l];
+          const double *fa = raw((int)(e & 0xFFu)), *fb = raw((int)((e >> 8) & 0xFFu));
+          for (int n = 0; n < ps.ncol[u]; ++n) {
+            const int col = ps.col0[u] + n;
+            const double* fc = raw(ps.colslot[col / 8] + col % 8);
+            double acc = 0.0;
+            for (int64_t x = 0; x < ncells; ++x) acc += fa[x] * fb[x] * fc[x];
+            partial[ip * (size_t)sc.pass_stride + ((size_t)(t * TEAMCOLS + ps.blk0[u] * 8 + n)) * 128 + l] = acc;
+          }
+        }
+      }
+  }
+  for (int t = 0; t < ntri; ++t) {
+    BSK_REQUIRE(sc.tri_slot[t] >= 0 && sc.tri_slot[t] < (int64_t)partial.size(), "bsk_tc_schedule_eval: slot out of range");
+    sums[t] = partial[(size_t)sc.tri_slot[t]];
+  }
+  return BSK_OK;
+}
+
 int bsk_cplan_set_path(bsk_cplan* cp, int path) {
   BSK_REQUIRE(cp && (path == 0 || path == 1), "bsk_cplan_set_path: path must be 0 (FP32 pipe) or 1 (tensor cores)");
   cp->path = path;

@@ -188,6 +188,13 @@ int bsk_cplan_set_path(bsk_cplan* cp, int path);
  * share a slot), sum of the units' accumulator columns, passes (kernel launches), all slots in
  * range, sum over units of max(11, columns/2) (MMA cycles per 8 cells and operand term)}. */
 int bsk_tc_schedule_info(int ntri, const int32_t* rows, int nrows, int64_t out[6]);
+/* Host only: evaluate the tensor-core schedule of a list on HOST float64 fields [nrows][ncells] by following
+ * its tables exactly as tc_contract_kernel does (lane -> pair rows, unit window column -> raw slot -> field
+ * row, (team, accumulator column, lane) -> partial slot, triangle -> slot), in plain float64 loops: sums[t] must
+ * equal sum_x f[r1] f[r2] f[r3] of triangle t.  Pins the schedule builders for any list shape without a GPU
+ * (tests/test_cabi.py); O(units * 128 * columns * ncells), meant for a few hundred cells. */
+int bsk_tc_schedule_eval(int ntri, const int32_t* rows, int nrows, int64_t ncells, const double* fields,
+                         double* sums);
 int bsk_cplan_path(const bsk_cplan* cp, int64_t out[3]);
 
 /* sums[j][t] = sum over local cells x of

@@ -117,3 +117,41 @@ def test_tensor_core_schedule_is_injective_and_pruned():
     # not eligible: too few triangles
     assert info(np.array([[a, a, a] for a in range(80)]), 80)["units"] == 0
     assert info(np.array([[0, 1, 2]]), 4)["units"] == 0
+
+
+def test_tensor_core_schedule_semantics_on_the_cpu():
+    """bsk_tc_schedule_eval follows the schedule tables the way tc_contract_kernel routes data (lane -> pair
+    rows, window column -> field row, (team, column, lane) -> slot, triangle -> slot) in float64 on the host:
+    every builder (two halves, class cover, multi-pass, cross lists, arbitrary row order) must deliver
+    sum_x f[r1] f[r2] f[r3] for every triangle.  Shapes the GPU tests do not run are covered here."""
+    import ctypes as C
+    import numpy as np
+    from bskit_b200 import _native
+    from bskit_b200.bins import generate_triangle_bin_list
+    lib = _native.lib()
+    kf = 2 * np.pi / 1000.0
+    rng = np.random.default_rng(5)
+
+    def check(tri, nrows, ncells=3):
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        f = rng.standard_normal((nrows, ncells))
+        out = np.zeros(len(tri))
+        rc = lib.bsk_tc_schedule_eval(len(tri), tri.ctypes.data_as(C.POINTER(C.c_int32)), nrows, ncells,
+                                      f.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0, _native.lib().bsk_last_error()
+        want = (f[tri[:, 0]] * f[tri[:, 1]] * f[tri[:, 2]]).sum(axis=1)
+        np.testing.assert_allclose(out, want, rtol=1e-12, atol=1e-12)
+
+    for nb in (12, 16, 20, 24, 28, 32, 36, 40, 48, 80):          # 1+1, 1+2, 2+1, 2+2 units, several passes
+        idx = np.asarray(generate_triangle_bin_list(kmin=0.5 * kf, kmax=(nb + 1.0) * kf, dk=kf, return_indices=True))
+        check(idx, (nb + 3) // 4 * 4)
+    # <AAB>: third row in a second 40-row segment
+    idx = np.asarray(generate_triangle_bin_list(kmin=0.5 * kf, kmax=41.0 * kf, dk=kf, num_fields=2, return_indices=True))
+    check(idx + np.array([0, 0, 40]), 80)
+    # the reference's production binning (80 bins, 24138 triangles)
+    kf75 = 2 * np.pi / 75.0
+    idx = np.asarray(generate_triangle_bin_list(0.5 * kf75, 23.5, kf75, num_lowk_bins=40, dk_high=6 * kf75, return_indices=True))
+    check(idx, 80, ncells=2)
+    # arbitrary row order and a non-closure selection rule
+    tri = np.array([[a, b, c] for a in range(40) for b in range(a, 40) for c in range(b, 40) if (a + b + c) % 3 == 0])
+    check(np.array([rng.permutation(t) for t in tri]), 40)
