@@ -393,7 +393,7 @@ class Engine:
     """Shell synthesis + triangle contraction on one (N, M, crop, precision) geometry."""
 
     def __init__(self, grid: GridChoice, boxsize, precision=nat.F32, device=None, group=None,
-                 backend_cls=NativeBackend, scratch_bytes=None, fft_precision=None,
+                 backend_cls=None, scratch_bytes=None, fft_precision=None,
                  accum_precision=None, no_prune=False, max_rows=None, contraction=None):
         self.grid = grid
         self.max_rows = max_rows
@@ -437,9 +437,11 @@ class Engine:
         extra = {} if contraction is None else {"contraction": contraction}
         if self.transposed:
             extra["transposed"] = True
-        self.backend = backend_cls(grid, self.boxsize, precision, self.world, self.rank,
-                                   self.device, self.chunk, fft_precision=fft_precision,
-                                   accum_precision=accum_precision, no_prune=no_prune, **extra)
+        # the CUDA backend unless the caller brings its own implementation of the stage interface
+        make_backend = backend_cls or NativeBackend
+        self.backend = make_backend(grid, self.boxsize, precision, self.world, self.rank,
+                                    self.device, self.chunk, fft_precision=fft_precision,
+                                    accum_precision=accum_precision, no_prune=no_prune, **extra)
         self.backend.group = self.group
         self.info = self.backend.info
         self.ncells = int(self.info.field_real_per_shell)

@@ -58,12 +58,6 @@ F32, F64 = 0, 1
 # --------------------------------------------------------------------------- #
 # engine management (lazy: importing this module needs neither torch nor a GPU)
 # --------------------------------------------------------------------------- #
-#: Test seam ONLY: tests/ may set this to a stand-in backend class to exercise the host logic
-#: (result dict, slicing, units, file formats, error paths) on a CPU-only box.  The product
-#: never sets it; with None every engine is the CUDA backend and raises without a GPU.
-_BACKEND_FOR_TESTS = None
-
-
 class _Session:
     """Engines for one (Nmesh, BoxSize) pair on this process's GPU."""
 
@@ -96,7 +90,7 @@ class _Session:
             # the few most recently used engines, close the rest (unbounded cache)
             while len(self._engines) >= self.MAX_ENGINES:
                 self._engines.pop(next(iter(self._engines))).close()
-            extra = {} if _BACKEND_FOR_TESTS is None else {"backend_cls": _BACKEND_FOR_TESTS}
+            extra = {}
             if self.contraction is not None:
                 extra["contraction"] = self.contraction
             e = self.eng.Engine(choice, self.boxsize, precision, device=self.device, group=self.group,

@@ -1,7 +1,7 @@
 """Host logic of the bskit.main mirror on a CPU-only box: result dict, index slicing, units,
 file formats, accumulation across calls, error paths.  The numeric stages are the numpy test
-double (tests/fake_backend.py) injected through the test seam main._BACKEND_FOR_TESTS; the
-product itself never runs without the CUDA library."""
+double (tests/fake_backend.py), patched over engine.NativeBackend by the fixture below; the
+product itself has no such switch and never runs without the CUDA library."""
 import os
 import pickle
 
@@ -10,6 +10,7 @@ import pytest
 import torch
 
 import bskit_b200 as bk
+from bskit_b200 import engine as bkengine
 from bskit_b200 import main as bkmain
 from fake_backend import FakeBackend
 from oracle import bskit_oracle as orc
@@ -20,7 +21,7 @@ BINS = dict(kmin=0.00314, kmax=0.1, dk=0.00628, num_lowk_bins=3, dk_high=0.01884
 
 @pytest.fixture(autouse=True)
 def cpu_backend(monkeypatch):
-    monkeypatch.setattr(bkmain, "_BACKEND_FOR_TESTS", FakeBackend)
+    monkeypatch.setattr(bkengine, "NativeBackend", FakeBackend)
     yield
     bk.clear_cache()
 
