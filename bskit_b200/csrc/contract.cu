@@ -680,6 +680,14 @@ int bsk_cplan_create(bsk_cplan** out, int ntri, const int32_t* rows, int nrows, 
     return rc;
   }
   if (!build_tc_schedule(cp, ntri, rows, nrows)) free_tc_schedule(cp);
+  // The tables above went up with cudaMemcpy from pageable memory: the call returns once the data is staged, the
+  // DMA itself is ordered in the legacy default stream only.  bsk_contract may run on a non-blocking stream
+  // (torch side streams) that does not wait for the legacy stream: finish the uploads here, once per schedule.
+  if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
+    set_error("bsk_cplan_create: upload of the schedule tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+    bsk_cplan_destroy(cp);
+    return BSK_ERR_CUDA;
+  }
   *out = cp;
   return BSK_OK;
 }

@@ -532,7 +532,10 @@ int bsk_plan_create(bsk_plan** out, const bsk_geometry* geom, const double* kx_t
       }
     }
     BSK_CUDA(cudaMalloc((void**)&p->d_wtab, sizeof(double2) * (size_t)M));
-    BSK_CUDA(cudaMemcpy(p->d_wtab, w.data(), sizeof(double2) * (size_t)M, cudaMemcpyHostToDevice));
+    // pageable source: the copy returns once staged and is ordered in the legacy stream only; the plan's
+    // stream may be a non-blocking one
+    BSK_CUDA(cudaMemcpyAsync(p->d_wtab, w.data(), sizeof(double2) * (size_t)M, cudaMemcpyHostToDevice, p->stream));
+    BSK_CUDA(cudaStreamSynchronize(p->stream));
   }
   f.fft_work_bytes = (int64_t)p->fft_work_bytes;
   *out = p;

@@ -874,7 +874,11 @@ def test_side_stream_measurement_matches_default_stream(bk, syn):
             with torch.cuda.stream(side):
                 second = run(contraction)
             third = run(contraction)
-            for other in (second, third):
+            # ... and with everything (plans, tables, schedules) CREATED under a non-blocking side stream
+            bk.clear_cache()
+            with torch.cuda.stream(torch.cuda.Stream()):
+                fourth = run(contraction)
+            for other in (second, third, fourth):
                 assert np.allclose(other[0], first[0], rtol=1e-12, atol=0)
                 assert np.array_equal(other[1], first[1])
                 assert np.allclose(other[2], first[2], rtol=1e-13, atol=0, equal_nan=True)
