@@ -879,8 +879,10 @@ def test_side_stream_measurement_matches_default_stream(bk, syn):
             with torch.cuda.stream(torch.cuda.Stream()):
                 fourth = run(contraction)
             for other in (second, third, fourth):
-                assert np.allclose(other[0], first[0], rtol=1e-12, atol=0)
+                # (a missing stream dependency shows up as garbage, not as rounding: the tolerance only leaves
+                # room for float64 partials folded in a different order)
+                assert np.allclose(other[0], first[0], rtol=1e-9, atol=1e-9 * np.sqrt(np.mean(first[0] ** 2)))
                 assert np.array_equal(other[1], first[1])
-                assert np.allclose(other[2], first[2], rtol=1e-13, atol=0, equal_nan=True)
+                assert np.allclose(other[2], first[2], rtol=1e-12, atol=0, equal_nan=True)
     finally:
         bk.set_gridinfo_cache(old)
